@@ -1,0 +1,177 @@
+/*
+ * mcb200 -- C ABI of the B200-native matchgate-circuit contraction library (libmcb200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of MatchCake (reference: /root/reference, v0.2.3):
+ * SPTM chaining -> covariance conjugation + Majorana sub-block gather -> Pfaffian, and the kernel
+ * Gram-matrix builder on top of it.  The reference has no native code of its own for this path: its
+ * arithmetic runs in PyTorch (einsum/linalg.det) and in the third-party wheel torchpfaffian; each entry
+ * point below cites the reference Python interface it replaces (paths relative to
+ * /root/reference/src/matchcake).  INTEGRATION.md shows the ctypes / torch.library binding a MatchCake
+ * maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the current CUDA device unless its name ends in _host;
+ *  - matrices are row-major FP64, batch axis leading;  N = qubits, d = 2N Majorana modes;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous
+ *    and stream-ordered, the library allocates nothing (scratch is passed in, see *_workspace_bytes);
+ *  - return value 0 = success; non-zero = error, message via mcb200_last_error() (thread local);
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef MCB200_H
+#define MCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB200_VERSION 100
+
+/* ------------------------------------------------------------------ circuit descriptor */
+/* Gate kinds.  Angle conventions follow the closed forms of
+ * operations/single_particle_transition_matrices/sptm_comp_rxrx.py:48-57, sptm_comp_ryry.py:53-67,
+ * sptm_comp_rzrz.py:51-67, sptm_fswap.py:12-27. */
+enum {
+  MCB200_GATE_RXRX = 0,   /* theta = params[b, off], phi = params[b, off+1]                         */
+  MCB200_GATE_RYRY = 1,
+  MCB200_GATE_RZRZ = 2,
+  MCB200_GATE_FSWAP = 3,  /* wires (wire0 < wire1), long range allowed; flag TRANSPOSE if descending */
+  MCB200_GATE_BLOCK4_CONST = 4, /* explicit real 4x4 block, 16 doubles at consts[off ..], shared by batch */
+  MCB200_GATE_BLOCK4_PARAM = 5  /* explicit real 4x4 block, 16 doubles at params[b, off ..]            */
+};
+#define MCB200_GATE_FLAG_TRANSPOSE 1
+
+typedef struct mcb200_gate {
+  int32_t kind;
+  int32_t wire0;     /* lowest wire index the block acts on; the 4x4 block sits at rows/cols 2*wire0   */
+  int32_t wire1;     /* FSWAP: the other wire (> wire0); otherwise wire0 + 1                          */
+  int32_t off;       /* column offset into params (or consts)                                        */
+  int32_t flags;
+  int32_t reserved;
+} mcb200_gate_t;
+
+/* A circuit = gates in APPLICATION order, grouped into layers of gates acting on disjoint wires:
+ * layer l = gates[layer_ptr[l] .. layer_ptr[l+1]).  The global SPTM is R = G_0 G_1 ... G_{n-1}
+ * (devices/nif_device.py:168-195, constants/__init__.py:33).  Optional affine map applied to every
+ * parameter column: angle = bias[c] + scale[c] * params[b, c]  (ml/kernels/fermionic_pqc_kernel.py:181). */
+typedef struct mcb200_circuit {
+  const mcb200_gate_t* gates;   /* device, n_gates                                                   */
+  const int32_t* layer_ptr;     /* device, n_layers + 1                                              */
+  int32_t n_gates;
+  int32_t n_layers;
+  int32_t n_qubits;
+  int32_t n_param_cols;         /* P: columns of params                                              */
+  const double* scale;          /* device, P or NULL                                                 */
+  const double* bias;           /* device, P or NULL                                                 */
+  const double* consts;         /* device or NULL                                                    */
+} mcb200_circuit_t;
+
+/* ------------------------------------------------------------------ library */
+int mcb200_version(void);
+const char* mcb200_last_error(void);
+int mcb200_device_count(void);
+
+/* ------------------------------------------------------------------ K1: SPTM chain */
+/* Columns of the global SPTM of a gate-list circuit: X[b] = R_b[:, cols] (d x m), one instance per
+ * batch row of params (B, P).  cols = NULL -> all d columns (X = R).  Replaces the per-gate Python
+ * loop NonInteractingFermionicDevice.apply_generator (devices/nif_device.py:281-347) ->
+ * contraction container (contraction_strategies/neighbours_strategy.py:13-26) -> Sptm.pad
+ * (single_particle_transition_matrix.py:379-402) -> update_single_particle_transition_matrix
+ * (nif_device.py:168-195), and NIFKernel._x_to_sptm (ml/kernels/nif_kernel.py:179-208). */
+int mcb200_circuit_columns(const mcb200_circuit_t* circuit_host, const double* params, int64_t B,
+                           const int32_t* cols, int32_t m, double* X_out, void* stream);
+
+/* Dense chain step: C[b] = op(A[b]) @ op(B[b]), (n x n), FP64 DMMA tiles.  Batch strides in elements
+ * (0 = operand shared by the whole batch).  Replaces utils/math.py:370-444 fermionic_operator_matmul /
+ * einsum("...ij,...jk->...ik") (nif_device.py:195, single_particle_transition_matrix.py:404-418) and
+ * the adjoint-then-multiply of NIFKernel.circuit (nif_kernel.py:159-177: R = b0 @ b1^T). */
+int mcb200_sptm_matmul(const double* A, int64_t strideA, int transA, const double* Bm, int64_t strideB,
+                       int transB, double* C, int64_t strideC, int32_t n, int64_t batch, void* stream);
+
+/* ------------------------------------------------------------------ K2: covariance conjugation + gather */
+/* Basis-state input |x>: cov[b] = (R_b^T Lambda_0 R_b)[maj, maj] from X[b] = R_b[:, maj] (d x m);
+ * Lambda_0 = (+)_k (-z_k) [[0,1],[-1,0]], z_k = (-1)^{bits[k]} (bits = NULL -> |0..0>).
+ * Replaces NonInteractingFermionicDevice.covariance_matrix (nif_device.py:1118-1131) +
+ * ProductStateProbabilityStrategy.extract_majorana_submatrix (product_state_strategy.py:95-110) for
+ * ProductState.from_basis_state inputs (product_state.py:46-79,203-205). */
+int mcb200_cov_basis(const double* X, const int8_t* bits, int64_t B, int32_t n_qubits, int32_t m,
+                     double* cov_out, void* stream);
+
+/* General input: cov[b] = (R~^T L0 R~)[idx, idx] for a dense initial (extended) covariance L0 (D x D,
+ * D = d or d+1; batch stride strideL0 = 0 if shared) and R (B, d, d) lifted by R (+) 1 when D = d+1
+ * (devices/expval_strategies/m_pfaffian/_extended_covariance.py:101-126, nif_device.py:1134-1164).
+ * idx = NULL -> all D indices.  workspace: mcb200_cov_dense_workspace_bytes. */
+int64_t mcb200_cov_dense_workspace_bytes(int64_t B, int32_t D, int32_t m);
+int mcb200_cov_dense(const double* R, int64_t strideR, const double* L0, int64_t strideL0, int64_t B,
+                     int32_t d, int32_t D, const int32_t* idx, int32_t m, double* cov_out,
+                     void* workspace, void* stream);
+
+/* ------------------------------------------------------------------ K3: Pfaffians */
+enum { MCB200_PF_ABS = 0, MCB200_PF_SIGNED = 1 };
+
+/* out[i] = scale * Pf(A[i]) (signed) or scale * |Pf(A[i])|, A (n, m, m) real skew-symmetric (only the
+ * strict upper triangle is read).  m = 0 -> 1, odd m -> 0.  Replaces utils.pfaffian / signed_pfaffian
+ * (utils/_pfaffian.py:17-36,78-119), i.e. torch_pfaffian.pfaffian(sign=True) and PfaffianDet.
+ * workspace: mcb200_pfaffian_workspace_bytes (0 for m <= 128). */
+int64_t mcb200_pfaffian_workspace_bytes(int64_t n, int32_t m);
+int mcb200_pfaffian(const double* A, int64_t n, int32_t m, int32_t mode, double scale, double* out,
+                    void* workspace, void* stream);
+
+/* out[b, q] = 2^-k |Pf(cov[b] + Lambda_y(outcomes[q]))|, cov (B, 2k, 2k), outcomes (Q, k) bits.
+ * normalize != 0 divides each row by its sum (qml.probs, nif_device.py:476-479).
+ * Replaces ProductStateProbabilityStrategy.__call__ (product_state_strategy.py:138-213) and
+ * LookupTableStrategy.__call__ (lookup_table_strategy.py:19-71) + base/lookup_table.py:132-205. */
+int mcb200_probs(const double* cov, const int8_t* outcomes, int64_t B, int32_t Q, int32_t k,
+                 int32_t normalize, double* out, void* stream);
+
+/* Pauli-sum read-out, two steps so that the summation order is deterministic:
+ *   feats[b, t] = Pf(cov[b][S_t, S_t])  for index_sets (T, s) int32 (sorted Majorana index sets of ONE parity
+ *   sector of size s; s = 0 -> 1, s = 2 -> direct gather), cov (B, D, D);
+ *   out[b] (+)= sum_t feats[b, t] * coeffs[t].
+ * Replaces sector_pfaffian_features (utils/_pfaffian.py:39-75) and the sector loop of
+ * MPfaffianExpvalStrategy.__call__ (m_pfaffian_expval_strategy.py:291-304). */
+int mcb200_sector_features(const double* cov, int64_t B, int32_t D, const int32_t* index_sets,
+                           int32_t T, int32_t s, double* feats, void* stream);
+int mcb200_rowdot(const double* feats, const double* coeffs, int64_t B, int32_t T, int32_t accumulate,
+                  double* out, void* stream);
+
+/* ------------------------------------------------------------------ fused projector expval */
+/* out[b] = <y| rho_b |y> on ALL wires for the circuit applied to the basis state |bits>:
+ * one kernel, SPTM columns + covariance + Pfaffian stay on chip (config C2 of BASELINE.json).
+ * Replaces the whole QNode execution path of SURVEY.md section 3.1. */
+int mcb200_circuit_expval_projector(const mcb200_circuit_t* circuit_host, const double* params,
+                                    int64_t B, const int8_t* init_bits, const int8_t* target_bits,
+                                    double* out, void* stream);
+
+/* ------------------------------------------------------------------ Gram builder */
+/* K[i, j] = scale * |Pf(cov0[i] + cov1[j])| for rows row_begin <= i < row_end (SURVEY.md A.5:
+ * equals P(0..0 | R_i R_j^T) of NIFKernel._compute_similarities_func, nif_kernel.py:210-221).
+ * mode MCB200_GRAM_REFERENCE reproduces GramMatrix.apply_/symmetrize_ (gram_matrix.py:84-161,177-201):
+ * only cells i>j (n0 >= n1) or j>i (n0 < n1) are evaluated, the other triangle of the leading
+ * min(n0,n1)^2 block is mirrored and the diagonal is 1.  MCB200_GRAM_FULL evaluates every cell.
+ * MCB200_GRAM_TRIANGLE evaluates the reference's cells only and writes nothing else (row-sharded multi-GPU
+ * builds: all-gather the row blocks, then call mcb200_gram_symmetrize once).
+ * K is (n0, n1) row-major with leading dimension ldk; only rows [row_begin,row_end) (and, in
+ * REFERENCE mode, their mirror cells) are written. */
+enum { MCB200_GRAM_REFERENCE = 0, MCB200_GRAM_FULL = 1, MCB200_GRAM_TRIANGLE = 2 };
+int64_t mcb200_gram_workspace_bytes(int64_t n0, int64_t n1, int32_t d);
+int mcb200_gram(const double* cov0, const double* cov1, int64_t n0, int64_t n1, int32_t d,
+                int64_t row_begin, int64_t row_end, int32_t mode, double scale, double* K,
+                int64_t ldk, void* workspace, void* stream);
+
+/* GramMatrix.symmetrize_ + _fill_diagonal_ (gram_matrix.py:127-161) on a device (n0, n1) matrix. */
+int mcb200_gram_symmetrize(double* K, int64_t n0, int64_t n1, int64_t ldk, void* stream);
+
+/* ------------------------------------------------------------------ instrumentation */
+/* Number of kernel launches issued by this library in the calling process since the last reset. */
+int64_t mcb200_launch_count(void);
+void mcb200_reset_launch_count(void);
+/* FP64 peak probes used by bench.py for the roofline denominators: runs a register-resident DFMA loop
+ * (kind 0) or a DMMA m8n8k4 loop (kind 1) and returns achieved TFLOP/s (< 0 on error). */
+double mcb200_probe_fp64_tflops(int32_t kind, int32_t iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB200_H */

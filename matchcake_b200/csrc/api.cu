@@ -1,0 +1,115 @@
+// Library plumbing: error reporting, launch accounting and FP64 peak probes.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace mcb200 {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launch_count{0};
+
+int set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return 1;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return set_error("%s: %s", what, cudaGetErrorString(e));
+}
+
+int check_launch(const char* what) {
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return check_cuda(cudaGetLastError(), what);
+}
+
+// ---- FP64 peak probes (roofline denominators; MEASURED_PEAKS.json only has HBM and bf16) ----------------
+__global__ void probe_dfma_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double x = 1.0000001, y = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+      a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void probe_dmma_kernel(double* out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) c[t][0] = c[t][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9 * (threadIdx.x + 1);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c[t][0]), "+d"(c[t][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) s += c[t][0] + c[t][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace mcb200
+
+using namespace mcb200;
+
+extern "C" int mcb200_version(void) { return MCB200_VERSION; }
+extern "C" const char* mcb200_last_error(void) { return g_last_error.c_str(); }
+extern "C" int mcb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+extern "C" int64_t mcb200_launch_count(void) { return g_launch_count.load(); }
+extern "C" void mcb200_reset_launch_count(void) { g_launch_count.store(0); }
+
+extern "C" double mcb200_probe_fp64_tflops(int32_t kind, int32_t iters, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  const int blocks = kNumSMs * 8, threads = 256;
+  double* buf = nullptr;
+  if (cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) {
+    set_error("probe: cudaMalloc failed");
+    return -1.0;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, st);
+    if (kind == 0) probe_dfma_kernel<<<blocks, threads, 0, st>>>(buf, iters);
+    else probe_dmma_kernel<<<blocks, threads, 0, st>>>(buf, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+  }
+  cudaError_t err = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  if (err != cudaSuccess) {
+    set_error("probe: %s", cudaGetErrorString(err));
+    return -1.0;
+  }
+  double flops;
+  if (kind == 0) flops = 2.0 * 64.0 * iters * (double)blocks * threads;            // 64 FMA / thread / iter
+  else flops = 2.0 * 8.0 * 256.0 * iters * (double)blocks * (threads / 32);         // 8 DMMA (8x8x4) / warp / iter
+  return flops / (best_ms * 1e-3) / 1e12;
+}

@@ -1,0 +1,358 @@
+// K1 (structured SPTM chain) + K2 (basis-state covariance conjugation) + fused projector expval.
+//
+// One thread block per circuit instance.  The block keeps X = R[:, cols] (d x m, FP64) in shared memory and
+// applies the gate list in REVERSE application order from the left:
+//     R = G_0 G_1 ... G_{n-1}   =>   R[:, cols] = G_0 (G_1 ( ... (G_{n-1} I[:, cols])))
+// Every gate is a 4x4 block on rows 2*wire0 .. 2*wire0+3, so one gate costs 8-16 FMA per column instead of
+// the 2 d^2 per column of the reference's dense padded product (devices/nif_device.py:195,
+// single_particle_transition_matrix.py:379-402).  Gates of one layer act on disjoint rows and run in parallel.
+#include "common.cuh"
+#include "pfaffian_dev.cuh"
+
+namespace mcb200 {
+
+struct CircuitDev {
+  const mcb200_gate_t* gates;
+  const int32_t* layer_ptr;
+  int n_gates, n_layers, n_qubits, n_param_cols;
+  const double* scale;
+  const double* bias;
+  const double* consts;
+};
+
+// Coefficients of one gate for one circuit instance: 16 doubles (row-major 4x4) for BLOCK4 kinds,
+// {c1, t1, c2, t2} for the three rotation kinds (two independent Givens pairs), nothing for FSWAP.
+__device__ __forceinline__ double load_angle(const CircuitDev& c, const double* prow, int col) {
+  double x = prow[col];
+  if (c.scale != nullptr) x = c.bias[col] + c.scale[col] * x;
+  return x;
+}
+
+__device__ void gate_coefficients(const CircuitDev& c, const mcb200_gate_t& g, const double* prow, double* out) {
+  switch (g.kind) {
+    case MCB200_GATE_RXRX: {  // sptm_comp_rxrx.py:48-57
+      double th = load_angle(c, prow, g.off) / 2, ph = load_angle(c, prow, g.off + 1) / 2;
+      double s, co;
+      sincos(ph - th, &s, &co);  // rows (0,3)
+      out[0] = co;
+      out[1] = -s;
+      sincos(ph + th, &s, &co);  // rows (1,2)
+      out[2] = co;
+      out[3] = s;
+      break;
+    }
+    case MCB200_GATE_RYRY: {  // sptm_comp_ryry.py:53-67
+      double th = load_angle(c, prow, g.off), ph = load_angle(c, prow, g.off + 1);
+      double s, co;
+      sincos((th + ph) / 2, &s, &co);  // rows (0,2)
+      out[0] = co;
+      out[1] = -s;
+      sincos((th - ph) / 2, &s, &co);  // rows (1,3)
+      out[2] = co;
+      out[3] = s;
+      break;
+    }
+    case MCB200_GATE_RZRZ: {  // sptm_comp_rzrz.py:51-67 (imaginary parts are identically ~0)
+      double th = load_angle(c, prow, g.off), ph = load_angle(c, prow, g.off + 1);
+      double s, co;
+      sincos((th + ph) / 2, &s, &co);  // rows (0,1)
+      out[0] = co;
+      out[1] = s;
+      sincos((th - ph) / 2, &s, &co);  // rows (2,3)
+      out[2] = co;
+      out[3] = s;
+      break;
+    }
+    case MCB200_GATE_BLOCK4_CONST: {
+      for (int i = 0; i < 16; ++i) {
+        int src = (g.flags & MCB200_GATE_FLAG_TRANSPOSE) ? (i % 4) * 4 + i / 4 : i;
+        out[i] = c.consts[g.off + src];
+      }
+      break;
+    }
+    case MCB200_GATE_BLOCK4_PARAM: {
+      for (int i = 0; i < 16; ++i) {
+        int src = (g.flags & MCB200_GATE_FLAG_TRANSPOSE) ? (i % 4) * 4 + i / 4 : i;
+        out[i] = prow[g.off + src];
+      }
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+// x <- G x on rows r0..r0+3 of column `col` of X.
+__device__ __forceinline__ void apply_gate_column(const mcb200_gate_t& g, const double* cf, double* X, int ld,
+                                                  int col, int d) {
+  double* x = X + (2 * g.wire0) * ld + col;
+  switch (g.kind) {
+    case MCB200_GATE_RXRX: {
+      double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
+      x[0] = cf[0] * x0 + cf[1] * x3;
+      x[3 * ld] = cf[0] * x3 - cf[1] * x0;
+      x[ld] = cf[2] * x1 + cf[3] * x2;
+      x[2 * ld] = cf[2] * x2 - cf[3] * x1;
+      break;
+    }
+    case MCB200_GATE_RYRY: {
+      double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
+      x[0] = cf[0] * x0 + cf[1] * x2;
+      x[2 * ld] = cf[0] * x2 - cf[1] * x0;
+      x[ld] = cf[2] * x1 + cf[3] * x3;
+      x[3 * ld] = cf[2] * x3 - cf[3] * x1;
+      break;
+    }
+    case MCB200_GATE_RZRZ: {
+      double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
+      x[0] = cf[0] * x0 + cf[1] * x1;
+      x[ld] = cf[0] * x1 - cf[1] * x0;
+      x[2 * ld] = cf[2] * x2 + cf[3] * x3;
+      x[3 * ld] = cf[2] * x3 - cf[3] * x2;
+      break;
+    }
+    case MCB200_GATE_FSWAP: {  // sptm_fswap.py:12-27
+      const int s = 2 * (g.wire1 - g.wire0 + 1);
+      if (s == 4) {
+        double x0 = x[0], x1 = x[ld];
+        x[0] = x[2 * ld];
+        x[ld] = x[3 * ld];
+        x[2 * ld] = x0;
+        x[3 * ld] = x1;
+      } else if (!(g.flags & MCB200_GATE_FLAG_TRANSPOSE)) {
+        // new[0:2] = old[s-2:s], new[i] = old[i-2]
+        double a = x[(s - 2) * ld], b = x[(s - 1) * ld];
+        for (int i = s - 1; i >= 2; --i) x[i * ld] = x[(i - 2) * ld];
+        x[0] = a;
+        x[ld] = b;
+      } else {
+        // new[i] = old[i+2], new[s-2:s] = old[0:2]
+        double a = x[0], b = x[ld];
+        for (int i = 0; i < s - 2; ++i) x[i * ld] = x[(i + 2) * ld];
+        x[(s - 2) * ld] = a;
+        x[(s - 1) * ld] = b;
+      }
+      break;
+    }
+    default: {  // BLOCK4_*
+      double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
+      x[0] = cf[0] * x0 + cf[1] * x1 + cf[2] * x2 + cf[3] * x3;
+      x[ld] = cf[4] * x0 + cf[5] * x1 + cf[6] * x2 + cf[7] * x3;
+      x[2 * ld] = cf[8] * x0 + cf[9] * x1 + cf[10] * x2 + cf[11] * x3;
+      x[3 * ld] = cf[12] * x0 + cf[13] * x1 + cf[14] * x2 + cf[15] * x3;
+      break;
+    }
+  }
+}
+
+// Build X = R[:, cols[c0 .. c0+mc)] in shared memory (d x mc, leading dimension ld).  coef: 16 doubles per gate
+// of the widest layer.  All threads of the block participate.
+__device__ void build_columns(const CircuitDev& c, const double* prow, const int32_t* cols, int c0, int mc,
+                              double* X, int ld, double* coef) {
+  const int d = 2 * c.n_qubits;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int idx = tid; idx < d * mc; idx += nthr) {
+    int r = idx / mc, cc = idx - r * mc;
+    int col = cols ? cols[c0 + cc] : c0 + cc;
+    X[r * ld + cc] = (r == col) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  for (int l = c.n_layers - 1; l >= 0; --l) {
+    const int g0 = c.layer_ptr[l], ng = c.layer_ptr[l + 1] - g0;
+    for (int g = tid; g < ng; g += nthr) gate_coefficients(c, c.gates[g0 + g], prow, coef + 16 * g);
+    __syncthreads();
+    for (int it = tid; it < ng * mc; it += nthr) {
+      int g = it / mc, cc = it - g * mc;
+      apply_gate_column(c.gates[g0 + g], coef + 16 * g, X, ld, cc, d);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- kernels
+__global__ void circuit_columns_kernel(CircuitDev c, const double* __restrict__ params, const int32_t* cols,
+                                       int m, int mc, int max_layer_gates, double* __restrict__ X_out) {
+  extern __shared__ double smem[];
+  const int d = 2 * c.n_qubits;
+  const long long b = blockIdx.x;
+  const int c0 = blockIdx.y * mc;
+  const int mcur = min(mc, m - c0);
+  double* X = smem;
+  double* coef = X + (size_t)d * mc;
+  build_columns(c, params + b * c.n_param_cols, cols, c0, mcur, X, mc, coef);
+  double* out = X_out + b * (long long)d * m;
+  for (int idx = threadIdx.x; idx < d * mcur; idx += blockDim.x) {
+    int r = idx / mcur, cc = idx - r * mcur;
+    out[(long long)r * m + c0 + cc] = X[r * mc + cc];
+  }
+}
+
+// cov[a][b] = sum_k s_k (X[2k][a] X[2k+1][b] - X[2k+1][a] X[2k][b]),  s_k = -z_k = -(-1)^{bits[k]}
+// (product_state.py:203-205 + nif_device.py:1131).  Strict upper triangle a < b only, computed as 2x2 tiles.
+__device__ void cov_basis_upper(const double* X, int ldx, int n_qubits, int m, const int8_t* bits, double* A,
+                                int lda) {
+  const int tiles = (m + 1) / 2;
+  const int items = tiles * tiles;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    int ta = it / tiles, tb = it - ta * tiles;
+    if (tb < ta) continue;
+    int a0 = 2 * ta, b0 = 2 * tb;
+    int a1 = min(a0 + 1, m - 1), b1 = min(b0 + 1, m - 1);
+    double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+    for (int k = 0; k < n_qubits; ++k) {
+      double sg = (bits != nullptr && bits[k]) ? 1.0 : -1.0;
+      const double* xe = X + (2 * k) * ldx;
+      const double* xo = xe + ldx;
+      double ea0 = sg * xe[a0], ea1 = sg * xe[a1], oa0 = sg * xo[a0], oa1 = sg * xo[a1];
+      double eb0 = xe[b0], eb1 = xe[b1], ob0 = xo[b0], ob1 = xo[b1];
+      s00 += ea0 * ob0 - oa0 * eb0;
+      s01 += ea0 * ob1 - oa0 * eb1;
+      s10 += ea1 * ob0 - oa1 * eb0;
+      s11 += ea1 * ob1 - oa1 * eb1;
+    }
+    if (a0 < b0) A[a0 * lda + b0] = s00;
+    if (a0 < b0 + 1 && b0 + 1 < m) A[a0 * lda + b0 + 1] = s01;
+    if (a0 + 1 < b0 && a0 + 1 < m) A[(a0 + 1) * lda + b0] = s10;
+    if (a0 + 1 < b0 + 1 && a0 + 1 < m && b0 + 1 < m) A[(a0 + 1) * lda + b0 + 1] = s11;
+  }
+}
+
+// K2 standalone: X (B, d, m) in global memory -> cov (B, m, m) full skew-symmetric matrix.
+__global__ void cov_basis_kernel(const double* __restrict__ X, const int8_t* bits, int n_qubits, int m,
+                                 double* __restrict__ cov_out) {
+  extern __shared__ double smem[];
+  const int d = 2 * n_qubits;
+  const long long b = blockIdx.x;
+  double* Xs = smem;            // d x m
+  double* A = Xs + (size_t)d * m;  // m x (m+1)
+  const int lda = m + 1;
+  const double* src = X + b * (long long)d * m;
+  for (int idx = threadIdx.x; idx < d * m; idx += blockDim.x) Xs[idx] = src[idx];
+  __syncthreads();
+  cov_basis_upper(Xs, m, n_qubits, m, bits, A, lda);
+  __syncthreads();
+  double* out = cov_out + b * (long long)m * m;
+  for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+    int i = idx / m, j = idx - i * m;
+    out[idx] = (i < j) ? A[i * lda + j] : (i > j ? -A[j * lda + i] : 0.0);
+  }
+}
+
+// Fused: circuit -> X (d x d) -> Lambda = X^T Lambda_0 X -> + Lambda_y -> 2^-N |Pf|.   One block per instance.
+__global__ void circuit_expval_projector_kernel(CircuitDev c, const double* __restrict__ params,
+                                                const int8_t* init_bits, const int8_t* target_bits,
+                                                double* __restrict__ out) {
+  extern __shared__ double smem[];
+  const int n = c.n_qubits, d = 2 * n;
+  const long long b = blockIdx.x;
+  double* X = smem;                    // d x d
+  double* A = X + (size_t)d * d;       // d x (d+1)
+  double* coef = A + (size_t)d * (d + 1);
+  double* red = coef;                  // reused after the circuit phase
+  const int lda = d + 1;
+  build_columns(c, params + b * c.n_param_cols, nullptr, 0, d, X, d, coef);
+  cov_basis_upper(X, d, n, d, init_bits, A, lda);
+  __syncthreads();
+  // + Lambda_y: (Lambda_y)[2j][2j+1] = -(-1)^{y_j}   (product_state_strategy.py:89-91)
+  for (int j = threadIdx.x; j < n; j += blockDim.x)
+    A[(2 * j) * lda + 2 * j + 1] += (target_bits != nullptr && target_bits[j]) ? 1.0 : -1.0;
+  __syncthreads();
+  double pf = block_pfaffian_upper(A, d, lda, red);
+  if (threadIdx.x == 0) out[b] = ldexp(fabs(pf), -n);
+}
+
+}  // namespace mcb200
+
+// ---------------------------------------------------------------------------------------------- C ABI
+using namespace mcb200;
+
+static int circuit_to_dev(const mcb200_circuit_t* h, CircuitDev* c) {
+  if (h == nullptr) return set_error("circuit descriptor is NULL");
+  if (h->n_qubits < 1) return set_error("n_qubits must be >= 1, got %d", h->n_qubits);
+  if (h->n_gates < 0 || h->n_layers < 0) return set_error("negative gate/layer count");
+  if (h->n_gates > 0 && (h->gates == nullptr || h->layer_ptr == nullptr))
+    return set_error("gates/layer_ptr must be device pointers when n_gates > 0");
+  if ((h->scale == nullptr) != (h->bias == nullptr)) return set_error("scale and bias must be given together");
+  c->gates = h->gates;
+  c->layer_ptr = h->layer_ptr;
+  c->n_gates = h->n_gates;
+  c->n_layers = h->n_layers;
+  c->n_qubits = h->n_qubits;
+  c->n_param_cols = h->n_param_cols;
+  c->scale = h->scale;
+  c->bias = h->bias;
+  c->consts = h->consts;
+  return 0;
+}
+
+extern "C" int mcb200_circuit_columns(const mcb200_circuit_t* circuit_host, const double* params, int64_t B,
+                                      const int32_t* cols, int32_t m, double* X_out, void* stream) {
+  CircuitDev c;
+  if (int rc = circuit_to_dev(circuit_host, &c)) return rc;
+  if (B < 0 || m < 0) return set_error("negative batch or column count");
+  if (B == 0 || m == 0) return 0;
+  if (X_out == nullptr) return set_error("X_out is NULL");
+  if (c.n_param_cols > 0 && params == nullptr) return set_error("params is NULL");
+  const int d = 2 * c.n_qubits;
+  const int max_layer_gates = c.n_qubits;  // a layer holds gates on disjoint wires: at most N of them
+  // column chunk so that X (d x mc) + coefficients fit in shared memory
+  const size_t coef_bytes = (size_t)max_layer_gates * 16 * sizeof(double);
+  int mc = m;
+  while ((size_t)d * mc * sizeof(double) + coef_bytes > 160 * 1024 && mc > 1) mc = (mc + 1) / 2;
+  const size_t smem = (size_t)d * mc * sizeof(double) + coef_bytes;
+  if (smem > (size_t)kMaxDynSmem) return set_error("circuit_columns: d=%d does not fit shared memory", d);
+  if (int rc = check_cuda(cudaFuncSetAttribute(circuit_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem), "cudaFuncSetAttribute(circuit_columns)"))
+    return rc;
+  const int chunks = (m + mc - 1) / mc;
+  const int threads = (d * mc >= 4096) ? 256 : 128;
+  for (int64_t b0 = 0; b0 < B; b0 += 2147483647LL) {  // gridDim.x limit
+    int64_t nb = B - b0 < 2147483647LL ? B - b0 : 2147483647LL;
+    dim3 grid((unsigned)nb, (unsigned)chunks);
+    circuit_columns_kernel<<<grid, threads, smem, as_stream(stream)>>>(
+        c, params + b0 * c.n_param_cols, cols, m, mc, max_layer_gates, X_out + b0 * (int64_t)d * m);
+    if (int rc = check_launch("circuit_columns_kernel")) return rc;
+  }
+  return 0;
+}
+
+extern "C" int mcb200_cov_basis(const double* X, const int8_t* bits, int64_t B, int32_t n_qubits, int32_t m,
+                                double* cov_out, void* stream) {
+  if (B < 0 || n_qubits < 1 || m < 0) return set_error("cov_basis: bad sizes");
+  if (B == 0 || m == 0) return 0;
+  if (X == nullptr || cov_out == nullptr) return set_error("cov_basis: NULL pointer");
+  const int d = 2 * n_qubits;
+  const size_t smem = ((size_t)d * m + (size_t)m * (m + 1)) * sizeof(double);
+  if (smem > (size_t)kMaxDynSmem)
+    return set_error("cov_basis: d=%d m=%d needs %zu B of shared memory; use mcb200_cov_dense", d, m, smem);
+  if (int rc = check_cuda(cudaFuncSetAttribute(cov_basis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem), "cudaFuncSetAttribute(cov_basis)"))
+    return rc;
+  cov_basis_kernel<<<(unsigned)B, 256, smem, as_stream(stream)>>>(X, bits, n_qubits, m, cov_out);
+  return check_launch("cov_basis_kernel");
+}
+
+extern "C" int mcb200_circuit_expval_projector(const mcb200_circuit_t* circuit_host, const double* params,
+                                               int64_t B, const int8_t* init_bits, const int8_t* target_bits,
+                                               double* out, void* stream) {
+  CircuitDev c;
+  if (int rc = circuit_to_dev(circuit_host, &c)) return rc;
+  if (B < 0) return set_error("negative batch");
+  if (B == 0) return 0;
+  if (out == nullptr) return set_error("out is NULL");
+  if (c.n_param_cols > 0 && params == nullptr) return set_error("params is NULL");
+  const int d = 2 * c.n_qubits;
+  const size_t coef_bytes = (size_t)(c.n_qubits > 4 ? c.n_qubits : 4) * 16 * sizeof(double);
+  const size_t smem = ((size_t)d * d + (size_t)d * (d + 1)) * sizeof(double) + coef_bytes;
+  if (smem > (size_t)kMaxDynSmem)
+    return set_error("circuit_expval_projector: %d qubits exceed the fused kernel's shared memory (max 59)",
+                     c.n_qubits);
+  if (int rc = check_cuda(cudaFuncSetAttribute(circuit_expval_projector_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(circuit_expval_projector)"))
+    return rc;
+  const int threads = d >= 64 ? 256 : 128;
+  circuit_expval_projector_kernel<<<(unsigned)B, threads, smem, as_stream(stream)>>>(c, params, init_bits,
+                                                                                   target_bits, out);
+  return check_launch("circuit_expval_projector_kernel");
+}

@@ -1,0 +1,189 @@
+// K1 (dense chain step) and K2 (dense covariance conjugation): strided-batched FP64 GEMM on the FP64 tensor
+// pipe (mma.sync.m8n8k4.f64 -> DMMA), tiles staged through shared memory.
+//
+//   C[b] (M x N) = op(A[b]) (M x K) @ op(B[b]) (K x N),   row-major, op = identity or transpose
+//
+// Block tile 64 x 64 x 16, 8 warps as 4 (M) x 2 (N); each warp owns a 16 x 32 patch = 2 x 4 DMMA tiles.
+// Shared-memory leading dimensions are chosen so that the 8-byte fragment reads of a half-warp hit 16
+// distinct bank pairs (ld = 4 mod 16).
+#include "common.cuh"
+
+namespace mcb200 {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int LDA_S = BK + 4;   // As[m][k]
+constexpr int LDB_S = BN + 4;   // Bs[k][n]
+
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+struct GemmArgs {
+  const double* A;
+  const double* B;
+  double* C;
+  long long sA, sB, sC;  // batch strides (elements), 0 = shared
+  int M, N, K;
+  int lda, ldb, ldc;
+};
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) bgemm_dmma_kernel(GemmArgs g) {
+  __shared__ double As[BM * LDA_S];
+  __shared__ double Bs[BK * LDB_S];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const long long b = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const double* A = g.A + b * g.sA;
+  const double* B = g.B + b * g.sB;
+  double* C = g.C + b * g.sC;
+
+  double acc[2][4][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // global -> register staging: 4 elements of each operand tile per thread
+  double ra[4], rb[4];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int e = tid + 256 * t;
+      // A tile element (mm, kk)
+      int mm, kk;
+      if (!TA) { mm = e / BK; kk = e % BK; } else { kk = e / BM; mm = e % BM; }
+      int gm = m0 + mm, gk = k0 + kk;
+      ra[t] = (gm < g.M && gk < g.K) ? (TA ? A[(long long)gk * g.lda + gm] : A[(long long)gm * g.lda + gk]) : 0.0;
+      // B tile element (kk, nn)
+      int nn;
+      if (!TB) { kk = e / BN; nn = e % BN; } else { nn = e / BK; kk = e % BK; }
+      int gn = n0 + nn;
+      gk = k0 + kk;
+      rb[t] = (gn < g.N && gk < g.K) ? (TB ? B[(long long)gn * g.ldb + gk] : B[(long long)gk * g.ldb + gn]) : 0.0;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      int e = tid + 256 * t;
+      int mm, kk, nn;
+      if (!TA) { mm = e / BK; kk = e % BK; } else { kk = e / BM; mm = e % BM; }
+      As[mm * LDA_S + kk] = ra[t];
+      if (!TB) { kk = e / BN; nn = e % BN; } else { nn = e / BK; kk = e % BK; }
+      Bs[kk * LDB_S + nn] = rb[t];
+    }
+  };
+
+  load_tiles(0);
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    store_tiles();
+    __syncthreads();
+    if (k0 + BK < g.K) load_tiles(k0 + BK);
+    const int gr = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < BK; ks += 4) {
+      double af[2], bf[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) af[i] = As[(wm * 16 + i * 8 + gr) * LDA_S + ks + tg];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Bs[(ks + tg) * LDB_S + wn * 32 + j * 8 + gr];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncthreads();
+  }
+  const int gr = lane >> 2, tg = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int r = m0 + wm * 16 + i * 8 + gr;
+      int c = n0 + wn * 32 + j * 8 + tg * 2;
+      if (r < g.M) {
+        if (c < g.N) C[(long long)r * g.ldc + c] = acc[i][j][0];
+        if (c + 1 < g.N) C[(long long)r * g.ldc + c + 1] = acc[i][j][1];
+      }
+    }
+}
+
+int launch_bgemm(const GemmArgs& g, int transA, int transB, long long batch, cudaStream_t st) {
+  if (batch == 0 || g.M == 0 || g.N == 0) return 0;
+  for (long long b0 = 0; b0 < batch; b0 += 65535) {
+    long long nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    GemmArgs h = g;
+    h.A += b0 * g.sA;
+    h.B += b0 * g.sB;
+    h.C += b0 * g.sC;
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, (unsigned)nb);
+    if (!transA && !transB) bgemm_dmma_kernel<false, false><<<grid, 256, 0, st>>>(h);
+    else if (transA && !transB) bgemm_dmma_kernel<true, false><<<grid, 256, 0, st>>>(h);
+    else if (!transA && transB) bgemm_dmma_kernel<false, true><<<grid, 256, 0, st>>>(h);
+    else bgemm_dmma_kernel<true, true><<<grid, 256, 0, st>>>(h);
+    if (int rc = check_launch("bgemm_dmma_kernel")) return rc;
+  }
+  return 0;
+}
+
+// X[b] (D x m) = Rlift[b][:, idx],  Rlift = R (+) 1 when D == d + 1  (_extended_covariance.py:101-126)
+__global__ void gather_columns_kernel(const double* R, long long sR, int d, int D, const int32_t* idx, int m,
+                                      double* X) {
+  const long long b = blockIdx.y;
+  const double* r = R + b * sR;
+  double* x = X + b * (long long)D * m;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < D * m; e += gridDim.x * blockDim.x) {
+    int row = e / m, c = e - row * m;
+    int col = idx ? idx[c] : c;
+    double v;
+    if (row < d && col < d) v = r[(long long)row * d + col];
+    else v = (row == col) ? 1.0 : 0.0;
+    x[e] = v;
+  }
+}
+
+}  // namespace mcb200
+
+using namespace mcb200;
+
+extern "C" int mcb200_sptm_matmul(const double* A, int64_t strideA, int transA, const double* Bm, int64_t strideB,
+                                  int transB, double* C, int64_t strideC, int32_t n, int64_t batch, void* stream) {
+  if (n < 0 || batch < 0) return set_error("sptm_matmul: negative size");
+  if (n == 0 || batch == 0) return 0;
+  if (A == nullptr || Bm == nullptr || C == nullptr) return set_error("sptm_matmul: NULL pointer");
+  GemmArgs g{A, Bm, C, strideA, strideB, strideC, n, n, n, n, n, n};
+  return launch_bgemm(g, transA, transB, batch, as_stream(stream));
+}
+
+extern "C" int64_t mcb200_cov_dense_workspace_bytes(int64_t B, int32_t D, int32_t m) {
+  return 2 * B * (int64_t)D * m * (int64_t)sizeof(double);
+}
+
+extern "C" int mcb200_cov_dense(const double* R, int64_t strideR, const double* L0, int64_t strideL0, int64_t B,
+                                int32_t d, int32_t D, const int32_t* idx, int32_t m, double* cov_out,
+                                void* workspace, void* stream) {
+  if (B < 0 || d < 1 || m < 0) return set_error("cov_dense: bad sizes");
+  if (D != d && D != d + 1) return set_error("cov_dense: D must be d or d+1 (got d=%d D=%d)", d, D);
+  if (B == 0 || m == 0) return 0;
+  if (R == nullptr || L0 == nullptr || cov_out == nullptr || workspace == nullptr)
+    return set_error("cov_dense: NULL pointer");
+  cudaStream_t st = as_stream(stream);
+  double* X = (double*)workspace;
+  double* Y = X + B * (int64_t)D * m;
+  for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+    int64_t nb = B - b0 < 65535 ? B - b0 : 65535;
+    dim3 grid((unsigned)((D * m + 255) / 256 < 64 ? (D * m + 255) / 256 : 64), (unsigned)nb);
+    gather_columns_kernel<<<grid, 256, 0, st>>>(R + b0 * strideR, strideR, d, D, idx, m, X + b0 * (int64_t)D * m);
+    if (int rc = check_launch("gather_columns_kernel")) return rc;
+  }
+  // Y = L0 @ X  (D x D @ D x m)
+  GemmArgs g1{L0, X, Y, strideL0, (long long)D * m, (long long)D * m, D, m, D, D, m, m};
+  if (int rc = launch_bgemm(g1, 0, 0, B, st)) return rc;
+  // cov = X^T @ Y  (m x D @ D x m)
+  GemmArgs g2{X, Y, cov_out, (long long)D * m, (long long)D * m, (long long)m * m, m, m, D, m, m, m};
+  return launch_bgemm(g2, 1, 0, B, st);
+}

@@ -1,0 +1,399 @@
+// K3: batched Pfaffians (plain, projector/probs read-out, Pauli-sector gather, Gram pairs).
+//
+// v1 layout: one warp per matrix, the matrix lives in that warp's slice of shared memory (strict upper
+// triangle only), Parlett-Reid elimination from pfaffian_dev.cuh.  Matrices larger than 128 x 128 use one
+// thread block per matrix with the working copy in a caller-provided global workspace (L2 resident).
+// "Loaders" form the matrix on the fly so that sums / gathers never round-trip through HBM:
+//   Plain   A[i]                              utils/_pfaffian.py:78-119
+//   Probs   cov[b] + Lambda_y(q)              product_state_strategy.py:196-213
+//   Sector  cov[b][S_t, S_t]                  utils/_pfaffian.py:39-75
+//   Gram    cov0[i] + cov1[j]                 nif_kernel.py:210-221 via SURVEY.md A.5
+#include "common.cuh"
+#include "pfaffian_dev.cuh"
+
+namespace mcb200 {
+
+// ------------------------------------------------------------------------------------------- loaders
+struct PlainLoader {
+  const double* A;
+  double* out;
+  double scale;
+  int mode;
+  __device__ void load(long long item, double* S, int lds, int m, int tid, int nthr) const {
+    const double* src = A + item * (long long)m * m;
+    for (int idx = tid; idx < m * m; idx += nthr) {
+      int i = idx / m, j = idx - i * m;
+      if (i < j) S[i * lds + j] = src[idx];
+    }
+  }
+  __device__ void store(long long item, double pf) const {
+    out[item] = scale * (mode == MCB200_PF_SIGNED ? pf : fabs(pf));
+  }
+};
+
+struct ProbsLoader {
+  const double* cov;       // (B, m, m)
+  const int8_t* outcomes;  // (Q, k)
+  double* out;             // (B, Q)
+  int Q, k;
+  __device__ void load(long long item, double* S, int lds, int m, int tid, int nthr) const {
+    long long b = item / Q;
+    int q = (int)(item - b * Q);
+    const double* src = cov + b * (long long)m * m;
+    const int8_t* y = outcomes + (long long)q * k;
+    for (int idx = tid; idx < m * m; idx += nthr) {
+      int i = idx / m, j = idx - i * m;
+      if (i < j) {
+        double v = src[idx];
+        if ((i & 1) == 0 && j == i + 1) v += y[i >> 1] ? 1.0 : -1.0;  // -(-1)^y
+        S[i * lds + j] = v;
+      }
+    }
+  }
+  __device__ void store(long long item, double pf) const { out[item] = ldexp(fabs(pf), -k); }
+};
+
+struct SectorLoader {
+  const double* cov;          // (B, D, D)
+  const int32_t* index_sets;  // (T, s)
+  double* feats;              // (B, T)
+  int D, T;
+  __device__ void load(long long item, double* S, int lds, int m, int tid, int nthr) const {
+    long long b = item / T;
+    int t = (int)(item - b * T);
+    const double* src = cov + b * (long long)D * D;
+    const int32_t* idx = index_sets + (long long)t * m;
+    for (int e = tid; e < m * m; e += nthr) {
+      int i = e / m, j = e - i * m;
+      if (i < j) S[i * lds + j] = src[(long long)idx[i] * D + idx[j]];
+    }
+  }
+  __device__ void store(long long item, double pf) const { feats[item] = pf; }
+};
+
+// ------------------------------------------------------------------------------------------- kernels
+template <class Loader, int kMaxChunks>
+__global__ void pfaffian_warp_kernel(Loader loader, long long n_items, int m) {
+  extern __shared__ double smem[];
+  const int lds = m + 1;
+  const int warps = blockDim.x >> 5;
+  double* S = smem + (size_t)warp_id() * m * lds;
+  const int lane = lane_id();
+  for (long long item = (long long)blockIdx.x * warps + warp_id(); item < n_items;
+       item += (long long)gridDim.x * warps) {
+    loader.load(item, S, lds, m, lane, 32);
+    __syncwarp();
+    double pf = warp_pfaffian_upper<kMaxChunks>(S, m, lds);
+    if (lane == 0) loader.store(item, pf);
+    __syncwarp();
+  }
+}
+
+template <class Loader>
+__global__ void pfaffian_block_global_kernel(Loader loader, long long n_items, int m, double* workspace) {
+  __shared__ double red[8];
+  const int lds = m + 1;
+  double* S = workspace + (size_t)blockIdx.x * m * lds;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    loader.load(item, S, lds, m, threadIdx.x, blockDim.x);
+    __syncthreads();
+    double pf = block_pfaffian_upper(S, m, lds, red);
+    if (threadIdx.x == 0) loader.store(item, pf);
+    __syncthreads();
+  }
+}
+
+__global__ void fill_kernel(double* out, long long n, double v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v;
+}
+
+__global__ void normalize_rows_kernel(double* p, long long B, int Q) {
+  // one warp per row (nif_device.py:478)
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp_id();
+  if (row >= B) return;
+  double* r = p + row * Q;
+  double s = 0.0;
+  for (int q = lane_id(); q < Q; q += 32) s += r[q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int q = lane_id(); q < Q; q += 32) r[q] = r[q] / s;
+}
+
+__global__ void sector_gather2_kernel(const double* cov, long long B, int D, const int32_t* index_sets, int T,
+                                      double* feats) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * T) return;
+  long long b = e / T;
+  int t = (int)(e - b * T);
+  feats[e] = cov[b * (long long)D * D + (long long)index_sets[2 * t] * D + index_sets[2 * t + 1]];
+}
+
+// out[b] (+)= sum_t feats[b, t] * coeffs[t]   (deterministic order; m_pfaffian_expval_strategy.py:304)
+__global__ void rowdot_kernel(const double* feats, const double* coeffs, long long B, int T, int accumulate,
+                              double* out) {
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp_id();
+  if (row >= B) return;
+  double s = 0.0;
+  for (int t = lane_id(); t < T; t += 32) s += feats[row * T + t] * coeffs[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane_id() == 0) out[row] = accumulate ? out[row] + s : s;
+}
+
+constexpr int kWarpKernelMaxM = 128;
+constexpr int kBlockGlobalCtas = 4 * kNumSMs;
+
+template <class Loader>
+static int launch_pfaffian(const Loader& loader, long long n_items, int m, double* workspace, cudaStream_t st,
+                           const char* what) {
+  if (n_items == 0) return 0;
+  if (m <= kWarpKernelMaxM) {
+    const size_t per_warp = (size_t)m * (m + 1) * sizeof(double);
+    int warps = (int)((200 * 1024) / (per_warp ? per_warp : 1));
+    if (warps > 8) warps = 8;
+    if (warps < 1) warps = 1;
+    const size_t smem = per_warp * warps;
+    long long blocks = (n_items + warps - 1) / warps;
+    const long long cap = 64LL * kNumSMs;  // persistent-ish grid, multiple of the SM count
+    if (blocks > cap) blocks = cap;
+    auto launch = [&](auto kernel) -> int {
+      if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                              "cudaFuncSetAttribute(pfaffian_warp)"))
+        return rc;
+      kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(loader, n_items, m);
+      return check_launch(what);
+    };
+    if (m <= 32) return launch(pfaffian_warp_kernel<Loader, 1>);
+    if (m <= 64) return launch(pfaffian_warp_kernel<Loader, 2>);
+    return launch(pfaffian_warp_kernel<Loader, 4>);
+  }
+  if (workspace == nullptr) return set_error("%s: m=%d needs a workspace (see *_workspace_bytes)", what, m);
+  long long blocks = n_items < kBlockGlobalCtas ? n_items : kBlockGlobalCtas;
+  pfaffian_block_global_kernel<Loader><<<(unsigned)blocks, 256, 0, st>>>(loader, n_items, m, workspace);
+  return check_launch(what);
+}
+
+static long long pfaffian_ws_bytes(long long n_items, int m) {
+  if (m <= kWarpKernelMaxM) return 0;
+  long long blocks = n_items < kBlockGlobalCtas ? n_items : kBlockGlobalCtas;
+  return blocks * (long long)m * (m + 1) * (long long)sizeof(double);
+}
+
+// ------------------------------------------------------------------------------------------- Gram
+// K[i][j] = scale |Pf(cov0[i] + cov1[j])|.  blockIdx.y = row (relative to row_begin), the warps of a block take
+// consecutive columns so that cov0[i] stays hot in L1/L2.
+struct GramArgs {
+  const double* cov0;
+  const double* cov1;
+  long long n0, n1;
+  int d;
+  long long row_begin;
+  int mode;
+  double scale;
+  double* K;
+  long long ldk;
+};
+
+__device__ __forceinline__ bool gram_cell_active(const GramArgs& g, long long i, long long j) {
+  if (j >= g.n1) return false;
+  if (g.mode == MCB200_GRAM_FULL) return true;
+  return (g.n0 < g.n1) ? (j > i) : (i > j);  // gram_matrix.py:191-195 (REFERENCE and TRIANGLE)
+}
+
+__device__ __forceinline__ void gram_store(const GramArgs& g, long long i, long long j, double v) {
+  g.K[i * g.ldk + j] = v;
+  if (g.mode == MCB200_GRAM_REFERENCE && j < g.n0 && i < g.n1) g.K[j * g.ldk + i] = v;  // gram_matrix.py:139-143
+}
+
+template <int kMaxChunks>
+__global__ void gram_warp_kernel(GramArgs g, long long rows, long long col_blocks) {
+  extern __shared__ double smem[];
+  const int m = g.d, lds = m + 1;
+  const int warps = blockDim.x >> 5;
+  double* S = smem + (size_t)warp_id() * m * lds;
+  const int lane = lane_id();
+  // flattened (row, column-block) index: gridDim.x can be huge, gridDim.y cannot
+  for (long long blk = blockIdx.x; blk < rows * col_blocks; blk += gridDim.x) {
+    const long long i = g.row_begin + blk / col_blocks;
+    const long long j = (blk % col_blocks) * warps + warp_id();
+    if (gram_cell_active(g, i, j)) {
+      const double* a = g.cov0 + i * (long long)m * m;
+      const double* b = g.cov1 + j * (long long)m * m;
+      for (int idx = lane; idx < m * m; idx += 32) {
+        int r = idx / m, c = idx - r * m;
+        if (r < c) S[r * lds + c] = a[idx] + b[idx];
+      }
+      __syncwarp();
+      double pf = warp_pfaffian_upper<kMaxChunks>(S, m, lds);
+      if (lane == 0) gram_store(g, i, j, g.scale * fabs(pf));
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void gram_block_global_kernel(GramArgs g, long long rows, double* workspace) {
+  __shared__ double red[8];
+  const int m = g.d, lds = m + 1;
+  double* S = workspace + (size_t)blockIdx.x * m * lds;
+  for (long long cell = blockIdx.x; cell < rows * g.n1; cell += gridDim.x) {
+    const long long i = g.row_begin + cell / g.n1;
+    const long long j = cell % g.n1;
+    if (!gram_cell_active(g, i, j)) continue;
+    const double* a = g.cov0 + i * (long long)m * m;
+    const double* b = g.cov1 + j * (long long)m * m;
+    for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+      int r = idx / m, c = idx - r * m;
+      if (r < c) S[r * lds + c] = a[idx] + b[idx];
+    }
+    __syncthreads();
+    double pf = block_pfaffian_upper(S, m, lds, red);
+    if (threadIdx.x == 0) gram_store(g, i, j, g.scale * fabs(pf));
+    __syncthreads();
+  }
+}
+
+__global__ void gram_symmetrize_kernel(double* K, long long n0, long long n1, long long ldk) {
+  // gram_matrix.py:127-161: mirror the computed triangle inside the leading min(n0,n1)^2 block, diagonal := 1
+  const long long q = n0 < n1 ? n0 : n1;
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= q * q) return;
+  long long i = e / q, j = e - i * q;
+  if (i == j) K[i * ldk + i] = 1.0;
+  else if (n0 < n1 ? (i > j) : (j > i)) K[i * ldk + j] = K[j * ldk + i];
+}
+
+__global__ void gram_diag_kernel(GramArgs g, long long row_end) {
+  long long i = g.row_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < row_end && i < g.n1) g.K[i * g.ldk + i] = 1.0;  // gram_matrix.py:147-161
+}
+
+}  // namespace mcb200
+
+// ---------------------------------------------------------------------------------------------- C ABI
+using namespace mcb200;
+
+extern "C" int64_t mcb200_pfaffian_workspace_bytes(int64_t n, int32_t m) { return pfaffian_ws_bytes(n, m); }
+
+extern "C" int mcb200_pfaffian(const double* A, int64_t n, int32_t m, int32_t mode, double scale, double* out,
+                               void* workspace, void* stream) {
+  if (n < 0 || m < 0) return set_error("pfaffian: negative size");
+  if (mode != MCB200_PF_ABS && mode != MCB200_PF_SIGNED) return set_error("pfaffian: unknown mode %d", mode);
+  if (n == 0) return 0;
+  if (out == nullptr) return set_error("pfaffian: out is NULL");
+  cudaStream_t st = as_stream(stream);
+  if (m == 0 || (m & 1)) {  // empty -> 1, odd -> 0 (tests/test_utils/test_pfaffian.py:66-75,121-127)
+    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, n, m == 0 ? scale : 0.0);
+    return check_launch("fill_kernel");
+  }
+  if (A == nullptr) return set_error("pfaffian: A is NULL");
+  PlainLoader ld{A, out, scale, mode};
+  return launch_pfaffian(ld, n, m, (double*)workspace, st, "pfaffian_kernel");
+}
+
+extern "C" int mcb200_probs(const double* cov, const int8_t* outcomes, int64_t B, int32_t Q, int32_t k,
+                            int32_t normalize, double* out, void* stream) {
+  if (B < 0 || Q < 0 || k < 1) return set_error("probs: bad sizes");
+  if (B == 0 || Q == 0) return 0;
+  if (cov == nullptr || outcomes == nullptr || out == nullptr) return set_error("probs: NULL pointer");
+  if (2 * k > kWarpKernelMaxM) return set_error("probs: k=%d measured wires exceed the fused limit of %d", k,
+                                                 kWarpKernelMaxM / 2);
+  cudaStream_t st = as_stream(stream);
+  ProbsLoader ld{cov, outcomes, out, Q, k};
+  if (int rc = launch_pfaffian(ld, (long long)B * Q, 2 * k, nullptr, st, "probs_kernel")) return rc;
+  if (normalize) {
+    normalize_rows_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(out, B, Q);
+    return check_launch("normalize_rows_kernel");
+  }
+  return 0;
+}
+
+extern "C" int mcb200_sector_features(const double* cov, int64_t B, int32_t D, const int32_t* index_sets,
+                                      int32_t T, int32_t s, double* feats, void* stream) {
+  if (B < 0 || T < 0 || s < 0 || D < 1) return set_error("sector_features: bad sizes");
+  if (B == 0 || T == 0) return 0;
+  if (feats == nullptr) return set_error("sector_features: feats is NULL");
+  cudaStream_t st = as_stream(stream);
+  const long long n = (long long)B * T;
+  if (s == 0 || (s & 1)) {
+    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(feats, n, s == 0 ? 1.0 : 0.0);
+    return check_launch("fill_kernel");
+  }
+  if (cov == nullptr || index_sets == nullptr) return set_error("sector_features: NULL pointer");
+  if (s == 2) {  // fast path utils/_pfaffian.py:70-72
+    sector_gather2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cov, B, D, index_sets, T, feats);
+    return check_launch("sector_gather2_kernel");
+  }
+  if (s > kWarpKernelMaxM) return set_error("sector_features: sector size %d > %d", s, kWarpKernelMaxM);
+  SectorLoader ld{cov, index_sets, feats, D, T};
+  return launch_pfaffian(ld, n, s, nullptr, st, "sector_pfaffian_kernel");
+}
+
+extern "C" int mcb200_rowdot(const double* feats, const double* coeffs, int64_t B, int32_t T, int32_t accumulate,
+                             double* out, void* stream) {
+  if (B < 0 || T < 0) return set_error("rowdot: bad sizes");
+  if (B == 0) return 0;
+  if (out == nullptr || (T > 0 && (feats == nullptr || coeffs == nullptr))) return set_error("rowdot: NULL pointer");
+  rowdot_kernel<<<(unsigned)((B + 7) / 8), 256, 0, as_stream(stream)>>>(feats, coeffs, B, T, accumulate, out);
+  return check_launch("rowdot_kernel");
+}
+
+extern "C" int64_t mcb200_gram_workspace_bytes(int64_t n0, int64_t n1, int32_t d) {
+  if (d <= kWarpKernelMaxM) return 0;
+  return (int64_t)kBlockGlobalCtas * d * (d + 1) * (int64_t)sizeof(double);
+}
+
+extern "C" int mcb200_gram(const double* cov0, const double* cov1, int64_t n0, int64_t n1, int32_t d,
+                           int64_t row_begin, int64_t row_end, int32_t mode, double scale, double* K, int64_t ldk,
+                           void* workspace, void* stream) {
+  if (n0 < 0 || n1 < 0 || d < 2 || (d & 1)) return set_error("gram: bad sizes (n0=%lld n1=%lld d=%d)",
+                                                               (long long)n0, (long long)n1, d);
+  if (row_begin < 0 || row_end > n0 || row_begin > row_end) return set_error("gram: bad row range");
+  if (mode != MCB200_GRAM_REFERENCE && mode != MCB200_GRAM_FULL && mode != MCB200_GRAM_TRIANGLE)
+    return set_error("gram: unknown mode %d", mode);
+  if (ldk < n1) return set_error("gram: ldk < n1");
+  const long long rows = row_end - row_begin;
+  if (rows == 0 || n1 == 0) return 0;
+  if (cov0 == nullptr || cov1 == nullptr || K == nullptr) return set_error("gram: NULL pointer");
+  cudaStream_t st = as_stream(stream);
+  GramArgs g{cov0, cov1, n0, n1, d, row_begin, mode, scale, K, ldk};
+  if (d <= kWarpKernelMaxM) {
+    const size_t per_warp = (size_t)d * (d + 1) * sizeof(double);
+    int warps = (int)((200 * 1024) / per_warp);
+    if (warps > 8) warps = 8;
+    if (warps < 1) warps = 1;
+    const size_t smem = per_warp * warps;
+    const long long col_blocks = (n1 + warps - 1) / warps;
+    long long blocks = rows * col_blocks;
+    const long long cap = 64LL * kNumSMs;
+    if (blocks > cap) blocks = cap;
+    auto launch = [&](auto kernel) -> int {
+      if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                              "cudaFuncSetAttribute(gram_warp)"))
+        return rc;
+      kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(g, rows, col_blocks);
+      return check_launch("gram_warp_kernel");
+    };
+    int rc = d <= 32 ? launch(gram_warp_kernel<1>) : d <= 64 ? launch(gram_warp_kernel<2>) : launch(gram_warp_kernel<4>);
+    if (rc) return rc;
+  } else {
+    if (workspace == nullptr) return set_error("gram: d=%d needs a workspace (mcb200_gram_workspace_bytes)", d);
+    long long blocks = rows * n1 < kBlockGlobalCtas ? rows * n1 : kBlockGlobalCtas;
+    gram_block_global_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, rows, (double*)workspace);
+    if (int rc = check_launch("gram_block_global_kernel")) return rc;
+  }
+  if (mode == MCB200_GRAM_REFERENCE) {
+    gram_diag_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(g, row_end);
+    return check_launch("gram_diag_kernel");
+  }
+  return 0;
+}
+
+extern "C" int mcb200_gram_symmetrize(double* K, int64_t n0, int64_t n1, int64_t ldk, void* stream) {
+  if (n0 < 0 || n1 < 0 || ldk < n1) return set_error("gram_symmetrize: bad sizes");
+  const long long q = n0 < n1 ? n0 : n1;
+  if (q == 0) return 0;
+  if (K == nullptr) return set_error("gram_symmetrize: K is NULL");
+  gram_symmetrize_kernel<<<(unsigned)((q * q + 255) / 256), 256, 0, as_stream(stream)>>>(K, n0, n1, ldk);
+  return check_launch("gram_symmetrize_kernel");
+}

@@ -1,0 +1,294 @@
+"""Thin torch-facing layer over the C ABI (include/mcb200.h).
+
+Every function takes CUDA ``float64`` tensors, launches hand-written sm_100a kernels from libmcb200.so on the
+current torch stream and returns new tensors.  PyTorch is used only for device memory and streams.  Nothing here
+computes on the CPU: a CPU tensor, a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CircuitStruct, Mcb200Error, check
+
+GATE_RXRX, GATE_RYRY, GATE_RZRZ, GATE_FSWAP, GATE_BLOCK4_CONST, GATE_BLOCK4_PARAM = range(6)
+FLAG_TRANSPOSE = 1
+PF_ABS, PF_SIGNED = 0, 1
+GRAM_REFERENCE, GRAM_FULL, GRAM_TRIANGLE = 0, 1, 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise Mcb200Error(f"{name} must live on a CUDA device: matchcake_b200 has no CPU path")
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    return t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> Optional[torch.Tensor]:
+    if nbytes <= 0:
+        return None
+    return torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+
+
+# ------------------------------------------------------------------------------------------------ circuits
+@dataclass
+class GateSpec:
+    """Host-side gate record (include/mcb200.h: mcb200_gate_t)."""
+
+    kind: int
+    wire0: int
+    wire1: int
+    off: int = 0
+    flags: int = 0
+
+    @property
+    def rows(self) -> Tuple[int, int]:
+        return 2 * self.wire0, 2 * self.wire1 + 2
+
+
+def schedule_layers(gates: Sequence[GateSpec]) -> Tuple[List[GateSpec], List[int]]:
+    """Greedy layering that preserves the product: consecutive gates on disjoint wires share a layer."""
+    layers: List[List[GateSpec]] = []
+    used: set = set()
+    for g in gates:
+        wires = set(range(g.wire0, g.wire1 + 1))
+        if not layers or (used & wires):
+            layers.append([])
+            used = set()
+        layers[-1].append(g)
+        used |= wires
+    flat: List[GateSpec] = []
+    ptr = [0]
+    for layer in layers:
+        flat.extend(layer)
+        ptr.append(len(flat))
+    return flat, ptr
+
+
+class CompiledCircuit:
+    """A gate-list circuit uploaded once to the device (gates in application order, R = G_0 G_1 ... G_{n-1})."""
+
+    def __init__(self, n_qubits: int, gates: Sequence[GateSpec], n_param_cols: int,
+                 scale: Optional[np.ndarray] = None, bias: Optional[np.ndarray] = None,
+                 consts: Optional[np.ndarray] = None, device: Optional[torch.device] = None):
+        if n_qubits < 1:
+            raise ValueError("n_qubits must be >= 1")
+        self.n_qubits = int(n_qubits)
+        self.n_param_cols = int(n_param_cols)
+        for g in gates:
+            if not (0 <= g.wire0 < g.wire1 < n_qubits):
+                raise ValueError(f"gate wires ({g.wire0},{g.wire1}) out of range for {n_qubits} qubits")
+            if g.kind != GATE_FSWAP and g.wire1 != g.wire0 + 1:
+                raise ValueError("two-qubit blocks act on consecutive wires")
+            width = 16 if g.kind == GATE_BLOCK4_PARAM else (2 if g.kind in (GATE_RXRX, GATE_RYRY, GATE_RZRZ) else 0)
+            if width and g.off + width > n_param_cols:
+                raise ValueError("gate parameter offset exceeds the parameter columns")
+        flat, ptr = schedule_layers(gates)
+        self.gates = flat
+        self.layer_ptr_host = ptr
+        self.device = torch.device(device if device is not None else "cuda")
+        arr = np.array([[g.kind, g.wire0, g.wire1, g.off, g.flags, 0] for g in flat], dtype=np.int32).reshape(-1, 6)
+        self.gates_dev = torch.from_numpy(arr).to(self.device)
+        self.layer_ptr_dev = torch.tensor(ptr, dtype=torch.int32, device=self.device)
+        f = lambda a: None if a is None else torch.as_tensor(np.asarray(a, dtype=np.float64)).to(self.device)
+        self.scale_dev, self.bias_dev, self.consts_dev = f(scale), f(bias), f(consts)
+        if (self.scale_dev is None) != (self.bias_dev is None):
+            raise ValueError("scale and bias must be given together")
+        self._struct = CircuitStruct(
+            gates=_ptr(self.gates_dev) if len(flat) else None, layer_ptr=_ptr(self.layer_ptr_dev),
+            n_gates=len(flat), n_layers=len(ptr) - 1, n_qubits=self.n_qubits, n_param_cols=self.n_param_cols,
+            scale=_ptr(self.scale_dev), bias=_ptr(self.bias_dev), consts=_ptr(self.consts_dev))
+
+    @property
+    def d(self) -> int:
+        return 2 * self.n_qubits
+
+    def _params(self, params: torch.Tensor) -> torch.Tensor:
+        params = _f64(params, "params")
+        if params.ndim != 2 or params.shape[1] != self.n_param_cols:
+            raise ValueError(f"params must have shape (B, {self.n_param_cols}), got {tuple(params.shape)}")
+        return params
+
+
+def circuit_columns(circ: CompiledCircuit, params: torch.Tensor, cols: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """X[b] = R_b[:, cols] (B, d, m); ``cols=None`` gives the full SPTM (B, d, d)."""
+    params = circ._params(params)
+    B = params.shape[0]
+    if cols is not None:
+        cols = cols.to(device=params.device, dtype=torch.int32).contiguous()
+        m = cols.numel()
+    else:
+        m = circ.d
+    out = torch.empty((B, circ.d, m), dtype=torch.float64, device=params.device)
+    check(_lib.load().mcb200_circuit_columns(C.byref(circ._struct), _ptr(params), B, _ptr(cols), m, _ptr(out),
+                                             _stream()))
+    return out
+
+
+def circuit_expval_projector(circ: CompiledCircuit, params: torch.Tensor, init_bits: Optional[torch.Tensor] = None,
+                             target_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """<y|rho_b|y> on all wires, one fused kernel (B,)."""
+    params = circ._params(params)
+    B = params.shape[0]
+    bits = lambda t: None if t is None else t.to(device=params.device, dtype=torch.int8).contiguous()
+    ib, tb = bits(init_bits), bits(target_bits)
+    out = torch.empty((B,), dtype=torch.float64, device=params.device)
+    check(_lib.load().mcb200_circuit_expval_projector(C.byref(circ._struct), _ptr(params), B, _ptr(ib), _ptr(tb),
+                                                      _ptr(out), _stream()))
+    return out
+
+
+def sptm_matmul(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False) -> torch.Tensor:
+    """Batched dense chain step C = op(a) @ op(b); a/b are (n,n) or (B,n,n) (a 2-D operand is shared)."""
+    a, b = _f64(a, "a"), _f64(b, "b")
+    n = a.shape[-1]
+    if a.shape[-2:] != (n, n) or b.shape[-2:] != (n, n):
+        raise ValueError("sptm_matmul expects square matrices of equal size")
+    batch = max(a.shape[0] if a.ndim == 3 else 1, b.shape[0] if b.ndim == 3 else 1)
+    for t in (a, b):
+        if t.ndim == 3 and t.shape[0] != batch:
+            raise ValueError("batch sizes differ")
+    sa = n * n if a.ndim == 3 else 0
+    sb = n * n if b.ndim == 3 else 0
+    out = torch.empty((batch, n, n), dtype=torch.float64, device=a.device)
+    check(_lib.load().mcb200_sptm_matmul(_ptr(a), sa, int(trans_a), _ptr(b), sb, int(trans_b), _ptr(out), n * n, n,
+                                         batch, _stream()))
+    return out if (a.ndim == 3 or b.ndim == 3) else out[0]
+
+
+# ------------------------------------------------------------------------------------------------ covariance
+def cov_basis(x: torch.Tensor, n_qubits: int, bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cov[b] = X_b^T Lambda_0(bits) X_b for X (B, d, m)."""
+    x = _f64(x, "x")
+    B, d, m = x.shape
+    if d != 2 * n_qubits:
+        raise ValueError("x must have 2*n_qubits rows")
+    ib = None if bits is None else bits.to(device=x.device, dtype=torch.int8).contiguous()
+    out = torch.empty((B, m, m), dtype=torch.float64, device=x.device)
+    check(_lib.load().mcb200_cov_basis(_ptr(x), _ptr(ib), B, n_qubits, m, _ptr(out), _stream()))
+    return out
+
+
+def cov_dense(r: torch.Tensor, l0: torch.Tensor, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cov[b] = (R~_b^T L0 R~_b)[idx, idx]; L0 is (D,D) or (B,D,D) with D = d or d+1 (extended covariance)."""
+    r, l0 = _f64(r, "r"), _f64(l0, "l0")
+    if r.ndim == 2:
+        r = r[None]
+    Br, d, _ = r.shape
+    D = l0.shape[-1]
+    Bl = l0.shape[0] if l0.ndim == 3 else 1
+    B = max(Br, Bl)
+    if Br not in (1, B) or Bl not in (1, B):
+        raise ValueError("batch sizes of r and l0 differ")
+    sr = d * d if (Br == B and B > 1) else 0
+    sl = D * D if (l0.ndim == 3 and Bl == B and B > 1) else 0
+    if idx is not None:
+        idx = idx.to(device=r.device, dtype=torch.int32).contiguous()
+        m = idx.numel()
+    else:
+        m = D
+    lib = _lib.load()
+    ws = _workspace(lib.mcb200_cov_dense_workspace_bytes(B, D, m), r.device)
+    out = torch.empty((B, m, m), dtype=torch.float64, device=r.device)
+    check(lib.mcb200_cov_dense(_ptr(r), sr, _ptr(l0), sl, B, d, D, _ptr(idx), m, _ptr(out), _ptr(ws), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ Pfaffians
+def pfaffian(a: torch.Tensor, signed: bool = False, scale: float = 1.0) -> torch.Tensor:
+    """Batched Pfaffian of real skew-symmetric matrices (..., m, m) -> (...)."""
+    a = _f64(a, "a")
+    m = a.shape[-1]
+    if a.shape[-2] != m:
+        raise ValueError("pfaffian expects square matrices")
+    batch_shape = a.shape[:-2]
+    n = int(np.prod(batch_shape)) if len(batch_shape) else 1
+    out = torch.empty((n,), dtype=torch.float64, device=a.device)
+    lib = _lib.load()
+    ws = _workspace(lib.mcb200_pfaffian_workspace_bytes(n, m), a.device)
+    check(lib.mcb200_pfaffian(_ptr(a), n, m, PF_SIGNED if signed else PF_ABS, float(scale), _ptr(out), _ptr(ws),
+                              _stream()))
+    return out.reshape(batch_shape)
+
+
+def probs(cov: torch.Tensor, outcomes: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+    """out[b, q] = 2^-k |Pf(cov[b] + Lambda_y(outcomes[q]))|; cov (B, 2k, 2k), outcomes (Q, k)."""
+    cov = _f64(cov, "cov")
+    outcomes = outcomes.to(device=cov.device, dtype=torch.int8).contiguous()
+    B, m, _ = cov.shape
+    Q, k = outcomes.shape
+    if m != 2 * k:
+        raise ValueError("cov must be (B, 2k, 2k) for outcomes (Q, k)")
+    out = torch.empty((B, Q), dtype=torch.float64, device=cov.device)
+    check(_lib.load().mcb200_probs(_ptr(cov), _ptr(outcomes), B, Q, k, int(normalize), _ptr(out), _stream()))
+    return out
+
+
+def sector_features(cov: torch.Tensor, index_sets: torch.Tensor) -> torch.Tensor:
+    """feats[b, t] = Pf(cov[b][S_t, S_t]); cov (B, D, D), index_sets (T, s)."""
+    cov = _f64(cov, "cov")
+    index_sets = index_sets.to(device=cov.device, dtype=torch.int32).contiguous()
+    B, D, _ = cov.shape
+    T, s = index_sets.shape
+    out = torch.empty((B, T), dtype=torch.float64, device=cov.device)
+    check(_lib.load().mcb200_sector_features(_ptr(cov), B, D, _ptr(index_sets), T, s, _ptr(out), _stream()))
+    return out
+
+
+def rowdot(feats: torch.Tensor, coeffs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b] (+)= sum_t feats[b,t] coeffs[t] (accumulates when ``out`` is given)."""
+    feats = _f64(feats, "feats")
+    coeffs = _f64(coeffs.to(feats.device), "coeffs")
+    B, T = feats.shape
+    acc = out is not None
+    if out is None:
+        out = torch.empty((B,), dtype=torch.float64, device=feats.device)
+    check(_lib.load().mcb200_rowdot(_ptr(feats), _ptr(coeffs), B, T, int(acc), _ptr(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ Gram
+def gram(cov0: torch.Tensor, cov1: torch.Tensor, scale: float, mode: int = GRAM_REFERENCE,
+         row_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K[i, j] = scale |Pf(cov0[i] + cov1[j])| with the reference's triangle/mirror/unit-diagonal rules."""
+    cov0, cov1 = _f64(cov0, "cov0"), _f64(cov1, "cov1")
+    n0, d, _ = cov0.shape
+    n1 = cov1.shape[0]
+    if cov1.shape[1:] != (d, d):
+        raise ValueError("cov0 and cov1 must hold matrices of the same size")
+    rb, re = (0, n0) if row_range is None else row_range
+    if out is None:
+        out = torch.zeros((n0, n1), dtype=torch.float64, device=cov0.device)
+    lib = _lib.load()
+    ws = _workspace(lib.mcb200_gram_workspace_bytes(n0, n1, d), cov0.device)
+    check(lib.mcb200_gram(_ptr(cov0), _ptr(cov1), n0, n1, d, rb, re, mode, float(scale), _ptr(out), out.stride(0),
+                          _ptr(ws), _stream()))
+    return out
+
+
+def gram_symmetrize(k: torch.Tensor) -> torch.Tensor:
+    check(_lib.load().mcb200_gram_symmetrize(_ptr(k), k.shape[0], k.shape[1], k.stride(0), _stream()))
+    return k
+
+
+def probe_fp64_tflops(kind: int, iters: int = 2000) -> float:
+    v = _lib.load().mcb200_probe_fp64_tflops(kind, iters, _stream())
+    if v < 0:
+        check(1)
+    return float(v)

@@ -1,0 +1,306 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes -> libmcb200.so), against the CPU oracle.
+
+Tolerance: north_star asks for 1e-10 relative on expectation values and Gram entries.  Probabilities of
+parity-forbidden outcomes are exactly 0 in exact arithmetic, where a relative bound is meaningless (SURVEY.md
+section 7 "hard parts"), so every comparison uses rtol=1e-10 with atol=1e-13."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import covariance as cv
+from oracle import gates, kernels, pfaffian, readout
+from oracle.gates import Op
+from tests.helpers import ops_to_circuit, random_skew, readme_ops
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-10, 1e-13
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_golden.json")))
+
+
+def dev(x, dtype=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device="cuda", dtype=dtype)
+
+
+def compiled(ops, n, batch, **kw):
+    from matchcake_b200 import ops as mops
+
+    g, params, consts = ops_to_circuit(ops, n, batch)
+    return mops.CompiledCircuit(n, g, params.shape[1], consts=consts, **kw), dev(params)
+
+
+# ------------------------------------------------------------------ K3
+@pytest.mark.parametrize("m", [2, 4, 6, 8, 16, 30, 32, 34, 62, 64, 66, 96, 128, 130, 256])
+@pytest.mark.parametrize("signed", [True, False])
+def test_pfaffian_matches_oracle(m, signed):
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(m)
+    n = 37 if m <= 64 else 5
+    a = random_skew(rng, (n, m, m)) / np.sqrt(m)
+    ref = pfaffian.pfaffian_signed(a)
+    if not signed:
+        ref = np.abs(ref)
+    out = mops.pfaffian(dev(a), signed=signed).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL * np.max(np.abs(ref)))
+
+
+def test_pfaffian_kats_and_edge_cases():
+    from matchcake_b200 import ops as mops
+
+    k = G["pfaffian_kats"]
+    assert mops.pfaffian(dev(k["two_by_two"]["matrix"]), signed=True).item() == pytest.approx(3.0, abs=1e-14)
+    a, b, c, d, e, f = k["four_by_four"]["abcdef"]
+    m4 = np.array([[0, a, b, c], [-a, 0, d, e], [-b, -d, 0, f], [-c, -e, -f, 0]])
+    assert mops.pfaffian(dev(m4), signed=True).item() == pytest.approx(8.0, abs=1e-13)
+    pm = np.array(k["pivot_swap"]["matrix"])
+    assert mops.pfaffian(dev(pm), signed=True).item() ** 2 == pytest.approx(np.linalg.det(pm), abs=1e-12)
+    assert mops.pfaffian(dev(np.zeros((3, 0, 0))), signed=True).cpu().tolist() == [1.0, 1.0, 1.0]  # empty -> 1
+    assert mops.pfaffian(dev(np.ones((2, 3, 3))), signed=True).cpu().tolist() == [0.0, 0.0]  # odd -> 0
+    assert mops.pfaffian(dev(np.zeros((2, 4, 4))), signed=False).cpu().tolist() == [0.0, 0.0]  # singular -> 0
+    assert mops.pfaffian(dev(np.zeros((0, 4, 4)))).shape == (0,)
+    # leading batch axes and scale
+    rng = np.random.default_rng(0)
+    x = random_skew(rng, (2, 3, 8, 8))
+    out = mops.pfaffian(dev(x), signed=True, scale=0.25).cpu().numpy()
+    np.testing.assert_allclose(out, 0.25 * pfaffian.pfaffian_signed(x), rtol=RTOL)
+
+
+def test_pfaffian_needs_pivoting():
+    """Zero leading entries force row/column swaps at every step."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(3)
+    m = 16
+    a = random_skew(rng, (9, m, m))
+    a[:, 0, 1] = a[:, 1, 0] = 0.0
+    a[:, 2, 3] = a[:, 3, 2] = 0.0
+    a[:, 0, 2:9] = 0.0
+    a[:, 2:9, 0] = 0.0
+    ref = pfaffian.pfaffian_signed(a)
+    np.testing.assert_allclose(mops.pfaffian(dev(a), signed=True).cpu().numpy(), ref, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(ref ** 2, np.linalg.det(a), rtol=1e-8)
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("n", [2, 4, 5, 16])
+@pytest.mark.parametrize("matchgate", [True, False])
+def test_circuit_sptm_readme(n, matchgate):
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(n)
+    B = 7
+    p = rng.uniform(0, 2 * np.pi, (B, 2))
+    ops = readme_ops(n, p, matchgate)
+    ref = np.broadcast_to(gates.chain(ops, n), (B, 2 * n, 2 * n))
+    circ, params = compiled(ops, n, B)
+    out = mops.circuit_columns(circ, params).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+    cols = torch.tensor([3, 0, 2 * n - 1], dtype=torch.int32)
+    sub = mops.circuit_columns(circ, params, cols).cpu().numpy()
+    np.testing.assert_allclose(sub, ref[:, :, [3, 0, 2 * n - 1]], rtol=RTOL, atol=ATOL)
+
+
+def test_circuit_sptm_general_gates():
+    """Long-range fSWAPs in both orientations, explicit 4x4 blocks (shared and per-instance), empty circuit."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(11)
+    n, B = 6, 5
+    blk = gates.random_sptm(2, seed=1)
+    blk_b = gates.random_sptm(2, seed=2, batch_size=B)
+    ops = [Op("SptmCompRyRy", (1, 2), params=rng.uniform(0, 6, (B, 2))), Op("SptmFSwap", (0, 4)),
+           Op("Sptm", (2, 3), matrix=blk), Op("SptmFSwap", (5, 2)), Op("SptmCompRzRz", (4, 5), params=rng.uniform(0, 6, (B, 2))),
+           Op("Sptm", (0, 1), matrix=blk_b), Op("SptmFSwap", (3, 2)), Op("SptmCompRxRx", (3, 4), params=rng.uniform(0, 6, (B, 2)))]
+    ref = gates.chain(ops, n, contraction=None)
+    circ, params = compiled(ops, n, B)
+    np.testing.assert_allclose(mops.circuit_columns(circ, params).cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    assert np.allclose(gates.chain(ops, n), ref, atol=1e-13)  # neighbours contraction == plain product
+    empty = mops.CompiledCircuit(3, [], 0)
+    out = mops.circuit_columns(empty, torch.zeros((2, 0), dtype=torch.float64, device="cuda")).cpu().numpy()
+    np.testing.assert_array_equal(out, np.broadcast_to(np.eye(6), (2, 6, 6)))
+
+
+@pytest.mark.parametrize("n,n_features", [(4, 4), (6, 12), (32, 64), (128, 128)])
+def test_kernel_ansatz_sptm(n, n_features):
+    """FermionicPQCKernel ansatz (affine map folded into the kernel) vs the oracle's _x_to_sptm."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(n)
+    B = 4 if n >= 32 else 9
+    x = rng.random((B, n_features))
+    k = kernels.FermionicPQCKernelOracle(n_qubits=n, rotations="X,Z").fit(x)
+    ref = k.x_to_sptm(x)
+    ops = k.ansatz(x)
+    g, params, consts = ops_to_circuit(ops, n, B)
+    circ = mops.CompiledCircuit(n, g, params.shape[1])
+    out = mops.circuit_columns(circ, dev(params)).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+
+
+# ------------------------------------------------------------------ K2 + read-out
+@pytest.mark.parametrize("n,k", [(4, 4), (6, 3), (16, 16), (20, 5)])
+def test_cov_basis_and_probs(n, k):
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(n + k)
+    B = 6
+    ops = readme_ops(n, rng.uniform(0, 2 * np.pi, (B, 2)), matchgate=False) + \
+        [Op("SptmCompRxRx", (w, w + 1), params=rng.uniform(0, 6, (B, 2))) for w in range(1, n - 1, 2)]
+    r = gates.chain(ops, n, contraction=None)
+    bits = rng.integers(0, 2, n)
+    wires = rng.permutation(n)[:k]
+    maj = readout.majorana_indices_of_wires(wires)
+    circ, params = compiled(ops, n, B)
+    x = mops.circuit_columns(circ, params, torch.as_tensor(maj, dtype=torch.int32))
+    cov = mops.cov_basis(x, n, torch.as_tensor(bits))
+    cov_ref = cv.evolve(cv.covariance_matrix(cv.amplitudes_from_basis_state(bits)), r)
+    np.testing.assert_allclose(cov.cpu().numpy(), cov_ref[:, maj[:, None], maj[None, :]], rtol=RTOL, atol=ATOL)
+    if k <= 5:
+        states = readout.states_to_binary(np.arange(2 ** k), k)
+    else:
+        states = rng.integers(0, 2, (11, k))
+    p = mops.probs(cov, torch.as_tensor(np.ascontiguousarray(states))).cpu().numpy()
+    # reference default path (complex lookup table) for basis-state inputs
+    ref = readout.probs_lookup_table(r, bits, states, wires).T
+    np.testing.assert_allclose(p, ref, rtol=RTOL, atol=ATOL)
+    if k <= 5:
+        pn = mops.probs(cov, torch.as_tensor(np.ascontiguousarray(states)), normalize=True).cpu().numpy()
+        np.testing.assert_allclose(pn, readout.analytic_probability(r, cv.amplitudes_from_basis_state(bits), wires),
+                                   rtol=RTOL, atol=ATOL)
+
+
+def test_fused_expval_projector_golden_and_batch():
+    from matchcake_b200 import ops as mops
+
+    g = G["joss_expval"]
+    circ, params = compiled(readme_ops(4, np.array([g["params"]])), 4, 1)
+    v = mops.circuit_expval_projector(circ, params).item()
+    assert f"{v:.4f}" == g["printed"]
+    rng = np.random.default_rng(1)
+    for n, B in [(4, 33), (16, 64), (7, 5)]:
+        p = rng.uniform(0, 2 * np.pi, (B, 2))
+        ops = readme_ops(n, p)
+        bits, tgt = rng.integers(0, 2, n), rng.integers(0, 2, n)
+        if n == 16:
+            bits = tgt = np.zeros(n, int)  # config C2
+        r = gates.chain(ops, n)
+        ref = readout.probs_lookup_table(r, bits, tgt, np.arange(n))
+        circ, params = compiled(ops, n, B)
+        out = mops.circuit_expval_projector(circ, params, torch.as_tensor(bits), torch.as_tensor(tgt)).cpu().numpy()
+        np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+
+
+def test_dense_path_tutorial_golden():
+    """Random dense SPTM, product-state inputs: probabilities and Pauli-sum expectation values of the tutorials."""
+    from matchcake_b200 import ops as mops
+
+    r = gates.random_sptm(3, seed=0)
+    th = np.pi / 3
+    mixed = np.array([[1.0, 1.0], [1.0, 0.0], [np.cos(th / 2), np.sin(th / 2)]], dtype=complex)
+    mixed /= np.linalg.norm(mixed, axis=1, keepdims=True)
+    plus = np.full((3, 2), 1 / np.sqrt(2), dtype=complex)
+    states = readout.states_to_binary(np.arange(8), 3)
+    h = G["hamiltonian"]
+    for amp, pkey, ekey in [(cv.amplitudes_from_basis_state([1, 0, 1]), "probs_basis_101", "expval_basis_101"),
+                            (plus, "probs_plus", "expval_plus"), (mixed, "probs_mixed", "expval_mixed")]:
+        cov = mops.cov_dense(dev(r), dev(cv.covariance_matrix(amp)))
+        p = mops.probs(cov, torch.as_tensor(np.ascontiguousarray(states)), normalize=True).cpu().numpy()[0]
+        np.testing.assert_array_equal(np.round(p, 6) + 0.0, np.asarray(G[pkey]["value"]))
+        ext0 = cv.extended_covariance_matrix(cv.covariance_matrix(amp), cv.displacement_vector(amp))
+        ext = mops.cov_dense(dev(r), dev(ext0))
+        np.testing.assert_allclose(ext.cpu().numpy()[0], cv.evolved_extended_covariance(amp, r), rtol=RTOL, atol=ATOL)
+        total = None
+        for sector, (idx, coeffs) in readout.pauli_sum_structure(h["pauli_words"], h["coeffs"], 3).items():
+            feats = mops.sector_features(ext, torch.as_tensor(idx, dtype=torch.int32))
+            total = mops.rowdot(feats, dev(coeffs), out=total)
+        assert round(total.item(), 6) == h[ekey]
+
+
+@pytest.mark.parametrize("n,terms", [(5, 40), (9, 25)])
+def test_sector_features_random_pauli_sums(n, terms):
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(n)
+    B = 4
+    r = gates.random_sptm(n, seed=n, batch_size=B)
+    amp = rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))
+    amp /= np.linalg.norm(amp, axis=1, keepdims=True)
+    words = ["".join(rng.choice(list("IXYZ"), n)) for _ in range(terms)]
+    coeffs = rng.standard_normal(terms)
+    ext_ref = cv.evolved_extended_covariance(amp, r)
+    ref = readout.expval_pauli_sum(ext_ref, words, coeffs)
+    ext0 = cv.extended_covariance_matrix(cv.covariance_matrix(amp), cv.displacement_vector(amp))
+    ext = mops.cov_dense(dev(r), dev(ext0))
+    total = None
+    for sector, (idx, sc) in readout.pauli_sum_structure(words, coeffs, n).items():
+        feats = mops.sector_features(ext, torch.as_tensor(idx.reshape(len(sc), sector), dtype=torch.int32))
+        total = mops.rowdot(feats, dev(sc), out=total)
+    np.testing.assert_allclose(total.cpu().numpy(), ref, rtol=RTOL, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,batch", [(8, 3), (32, 5), (70, 2), (128, 2)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+def test_sptm_matmul(n, batch, ta, tb):
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(n)
+    a, b = rng.standard_normal((batch, n, n)), rng.standard_normal((batch, n, n))
+    ref = (np.swapaxes(a, 1, 2) if ta else a) @ (np.swapaxes(b, 1, 2) if tb else b)
+    out = mops.sptm_matmul(dev(a), dev(b), ta, tb).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-12)
+    shared = mops.sptm_matmul(dev(a), dev(b[0]), ta, tb).cpu().numpy()
+    np.testing.assert_allclose(shared, (np.swapaxes(a, 1, 2) if ta else a) @ (b[0].T if tb else b[0]), rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------ Gram
+@pytest.mark.parametrize("n,shape", [(4, (13, 13)), (4, (9, 14)), (4, (14, 9)), (16, (10, 10)), (32, (6, 6)), (70, (3, 4))])
+def test_gram_matches_reference_formulation(n, shape):
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(n)
+    nf = 2 * n if n <= 32 else n
+    x0, x1 = rng.random((shape[0], nf)), rng.random((shape[1], nf))
+    k = kernels.FermionicPQCKernelOracle(n_qubits=n, rotations="X,Z").fit(x0)
+    ref = k.gram(x0, x1, float32_store=False)
+    lam0 = cv.covariance_matrix(cv.amplitudes_from_basis_state(np.zeros(n, int)))
+    c0, c1 = cv.evolve(lam0, k.x_to_sptm(x0)), cv.evolve(lam0, k.x_to_sptm(x1))
+    out = mops.gram(dev(c0), dev(c1), scale=2.0 ** -n).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+    full = mops.gram(dev(c0), dev(c1), scale=2.0 ** -n, mode=mops.GRAM_FULL).cpu().numpy()
+    idx = np.stack(np.meshgrid(np.arange(shape[0]), np.arange(shape[1]), indexing="ij"), -1).reshape(-1, 2)
+    np.testing.assert_allclose(full.reshape(-1), k.pair_expvals(k.x_to_sptm(x0), k.x_to_sptm(x1), idx), rtol=RTOL, atol=ATOL)
+    # row-sharded triangle + symmetrize == single call
+    tri = torch.zeros(shape, dtype=torch.float64, device="cuda")
+    h = shape[0] // 2
+    mops.gram(dev(c0), dev(c1), scale=2.0 ** -n, mode=mops.GRAM_TRIANGLE, row_range=(0, h), out=tri)
+    mops.gram(dev(c0), dev(c1), scale=2.0 ** -n, mode=mops.GRAM_TRIANGLE, row_range=(h, shape[0]), out=tri)
+    np.testing.assert_array_equal(mops.gram_symmetrize(tri).cpu().numpy(), out)
+
+
+def test_gram_identical_rows_is_all_ones():
+    """tests/test_ml/test_kernels/test_fermionic_pqc_kernel.py:111-115."""
+    from matchcake_b200 import ops as mops
+
+    n = 8
+    x = np.full((5, 2 * n), 0.37)
+    k = kernels.FermionicPQCKernelOracle(n_qubits=n, rotations="Y,Z").fit(x)
+    lam0 = cv.covariance_matrix(cv.amplitudes_from_basis_state(np.zeros(n, int)))
+    c = dev(cv.evolve(lam0, k.x_to_sptm(x)))
+    np.testing.assert_allclose(mops.gram(c, c, scale=2.0 ** -n).cpu().numpy(), 1.0, rtol=1e-12)
+
+
+def test_errors_are_loud():
+    from matchcake_b200 import ops as mops
+    from matchcake_b200._lib import Mcb200Error
+
+    with pytest.raises(Mcb200Error):
+        mops.pfaffian(torch.zeros((2, 4, 4), dtype=torch.float64))  # CPU tensor: no CPU path
+    with pytest.raises(ValueError):
+        mops.CompiledCircuit(3, [mops.GateSpec(mops.GATE_RXRX, 2, 3, 0)], 2)
+    with pytest.raises(Mcb200Error):
+        mops.probs(torch.zeros((1, 140, 140), dtype=torch.float64, device="cuda"),
+                   torch.zeros((1, 70), dtype=torch.int8, device="cuda"))

@@ -1,0 +1,50 @@
+"""CPU-side checks of the drop-in boundary: libmcb200.so loads and exports exactly what include/mcb200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mcb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mcb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from matchcake_b200 import _lib, build
+
+    build.build()
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/mcb200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.mcb200_version() == 100
+    assert lib.mcb200_launch_count() >= 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    from matchcake_b200 import ops as mops
+    from matchcake_b200._lib import Mcb200Error
+
+    with pytest.raises(Mcb200Error):
+        mops.pfaffian(torch.zeros((1, 2, 2), dtype=torch.float64))
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reference the oracle (tier rule 3)."""
+    pkg = os.path.join(ROOT, "matchcake_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "/root/reference" not in txt or f.endswith((".cu", ".cuh", ".h", ".py")) and "import" not in txt.split("/root/reference")[0][-40:]
