@@ -1,0 +1,595 @@
+"""``NonInteractingFermionicDevice`` -- the reference's device API on top of the CUDA library.
+
+Mirrors the MatchCake-native surface of /root/reference/src/matchcake/devices/nif_device.py that the hot path
+sits behind: ``apply_generator`` (:281), ``execute_generator`` (:580), ``execute_output``
+(:623), ``get_states_probability`` (:742), ``analytic_probability`` (:430), ``exact_expval`` (:506), ``probability``
+(:885), ``reset`` (:911), properties ``global_sptm`` (:1167), ``covariance_matrix`` (:1118),
+``extended_covariance_matrix`` (:1134), ``transition_matrix`` (:1277), and ``states_to_binary`` (:151).
+
+Difference in mechanism, not in results: the reference multiplies a dense padded ``(B, 2N, 2N)`` matrix per
+contracted gate group in Python; this device only RECORDS the operation stream and compiles it into one circuit
+descriptor.  The SPTM chain, the covariance conjugation + Majorana gather and the Pfaffians then run as CUDA
+kernels (libmcb200), fused into a single launch for full-register projectors.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict, defaultdict
+from typing import Any, Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import observables as obs_mod
+from . import ops as _ops
+from .operations import (BasisState, CompRotation, CompZX, MatchgateOperation, Operation, ProductState,
+                         SingleParticleTransitionMatrixOperation, SptmAngleEmbedding, SptmCompZX,
+                         _SptmCompRotation, _as_f64_tensor, _wires_tuple, make_wires_continuous)
+from .utils.jordan_wigner import JordanWigner, extend_majorana_indices
+
+_UNSET = object()
+
+CONTRACTION_STRATEGIES = {None: "none", "none": "none", "neighbours": "neighbours", "horizontal": "horizontal",
+                          "vertical": "vertical", "forward": "forward"}
+PROBABILITY_STRATEGIES = {"lookuptable": "LookupTable", "productstate": "ProductState", "b200": "B200"}
+
+
+class DeviceError(Exception):
+    """Unsupported operation / state preparation (stands in for ``pennylane.exceptions.DeviceError``)."""
+
+
+def _is_projector(o) -> bool:
+    return isinstance(o, obs_mod.Projector) or type(o).__name__ in ("BasisStateProjector", "Projector")
+
+
+class _PauliStructureCache:
+    """Coefficient-independent Pauli -> Majorana decomposition, LRU + lock (m_pfaffian_expval_strategy.py:41-221)."""
+
+    MAXSIZE = 64
+    _cache: "OrderedDict[tuple, dict]" = OrderedDict()
+    import threading as _threading
+
+    _lock = _threading.Lock()
+
+    @classmethod
+    def clear(cls):
+        with cls._lock:
+            cls._cache.clear()
+
+    @classmethod
+    def get(cls, pauli_strs: Tuple[str, ...], n_qubits: int) -> dict:
+        key = (pauli_strs, n_qubits)
+        with cls._lock:
+            hit = cls._cache.get(key)
+            if hit is not None:
+                cls._cache.move_to_end(key)
+                return hit
+        jw = JordanWigner(n_qubits)
+        wires = list(range(n_qubits))
+        by_sector: dict = {}
+        for t, ps in enumerate(pauli_strs):
+            mu, alpha = jw.pauli_to_majorana(ps, wires)
+            ext, phase = extend_majorana_indices(mu, alpha, 2 * n_qubits)
+            idx, ph, terms = by_sector.setdefault(len(ext), ([], [], []))
+            idx.append(ext)
+            ph.append(phase)
+            terms.append(t)
+        structure = {}
+        for sector, (idx, ph, terms) in by_sector.items():
+            index_sets = np.stack(idx).astype(np.int32) if sector else np.zeros((len(idx), 0), dtype=np.int32)
+            structure[sector] = (index_sets, np.asarray(ph, dtype=complex), np.asarray(terms, dtype=int),
+                                 (-1j) ** (sector // 2))
+        with cls._lock:
+            cls._cache[key] = structure
+            while len(cls._cache) > cls.MAXSIZE:
+                cls._cache.popitem(last=False)
+        return structure
+
+
+class NonInteractingFermionicDevice:
+    name = "nif.qubit"
+    R_DTYPE = torch.float64
+    C_DTYPE = torch.complex128
+    DEFAULT_PROB_STRATEGY = "LookupTable"
+    DEFAULT_CONTRACTION_METHOD = "neighbours"
+    FUSED_MAX_QUBITS = 59  # shared-memory limit of the fused projector kernel
+
+    @staticmethod
+    def states_to_binary(samples: np.ndarray, num_wires: int, dtype: type = np.int64) -> np.ndarray:
+        """Integer outcome indices -> bits, MSB first."""
+        shifts = np.arange(num_wires - 1, -1, -1, dtype=dtype)
+        return ((np.asarray(samples, dtype=dtype)[..., None] >> shifts) & 1).astype(dtype)
+
+    @classmethod
+    def update_single_particle_transition_matrix(cls, old_sptm, new_sptm):
+        """``old @ new`` (nif_device.py:168-195) on the GPU."""
+        mat = lambda x: x.matrix() if isinstance(x, Operation) else x
+        new = _as_f64_tensor(mat(new_sptm), device="cuda")
+        if old_sptm is None:
+            return new
+        return _ops.sptm_matmul(_as_f64_tensor(mat(old_sptm), device="cuda"), new)
+
+    def __init__(self, wires: Optional[Union[int, Sequence]] = None, *, shots: Optional[int] = None, **kwargs):
+        if wires is not None:
+            n = wires if isinstance(wires, (int, np.integer)) else len(list(wires))
+            assert n > 1, "At least two wires are required for this device."
+        if shots is not None:
+            raise NotImplementedError("Shot-based sampling is outside the B200 hot path (SURVEY.md 8f rank 3).")
+        self._wires: Optional[Tuple] = None
+        if wires is not None:
+            self._wires = tuple(range(wires)) if isinstance(wires, (int, np.integer)) else _wires_tuple(wires)
+        self._init_kwargs = kwargs
+        self.R_DTYPE = kwargs.get("r_dtype") or type(self).R_DTYPE
+        self.C_DTYPE = kwargs.get("c_dtype") or type(self).C_DTYPE
+        strat = kwargs.get("prob_strategy", self.DEFAULT_PROB_STRATEGY)
+        if isinstance(strat, str):
+            if strat.lower() not in PROBABILITY_STRATEGIES:
+                raise ValueError(f"Unknown probability strategy {strat!r}; available: {sorted(PROBABILITY_STRATEGIES.values())} "
+                                 "(ExplicitSum/CliffordSum are exponential cross-check paths and are not part of this build)")
+            strat = PROBABILITY_STRATEGIES[strat.lower()]
+        self.prob_strategy = strat
+        cs = kwargs.get("contraction_strategy", self.DEFAULT_CONTRACTION_METHOD)
+        key = cs.lower() if isinstance(cs, str) else cs
+        if key not in CONTRACTION_STRATEGIES:
+            raise ValueError(f"Unknown contraction strategy {cs!r}; available: {sorted(k for k in CONTRACTION_STRATEGIES if k)}")
+        self.contraction_strategy = CONTRACTION_STRATEGIES[key]
+        self.torch_device = torch.device(kwargs.get("device", "cuda"))
+        self.output_device = kwargs.get("output_device", "cpu")
+        self.show_progress = kwargs.get("show_progress", False)
+        self.apply_metadata: defaultdict = defaultdict()
+        self._circuit_cache: "OrderedDict[tuple, _ops.CompiledCircuit]" = OrderedDict()
+        self._state_prep_op: Optional[ProductState] = None
+        self._program: List[Operation] = []
+        self._sptm: Optional[torch.Tensor] = None
+        self._compiled = None
+        self._batched = False
+        if self._wires is not None:
+            self._state_prep_op = ProductState.from_basis_state(np.zeros(self.num_wires, dtype=int), wires=self.wires)
+
+    # ------------------------------------------------------------------ bookkeeping
+    @property
+    def wires(self) -> Tuple:
+        return self._wires
+
+    @property
+    def num_wires(self) -> Optional[int]:
+        return None if self._wires is None else len(self._wires)
+
+    @property
+    def shots(self):
+        return None
+
+    @property
+    def state_prep_op(self):
+        return self._state_prep_op
+
+    @property
+    def state(self):
+        raise NotImplementedError("The NIF device does not support dense state representation. "
+                                  "It would require an exponential amount of memory.")
+
+    def reset(self) -> None:
+        self._program = []
+        self._sptm = None
+        self._compiled = None
+        self._batched = False
+        self.apply_metadata = defaultdict()
+        if self._wires is not None:
+            self._state_prep_op = ProductState.from_basis_state(np.zeros(self.num_wires, dtype=int), wires=self.wires)
+
+    def _wire_index(self, w) -> int:
+        try:
+            return self._wires.index(w)
+        except ValueError:
+            raise DeviceError(f"Wire {w!r} is not a wire of this device ({self._wires}).")
+
+    def _out(self, t: torch.Tensor, squeeze_batch: bool = False):
+        if squeeze_batch and not self._batched:
+            t = t.squeeze(-1) if t.ndim and t.shape[-1] == 1 else t
+        t = t.to(self.R_DTYPE)
+        return t if self.output_device in (None, "cuda") else t.to(self.output_device)
+
+    # ------------------------------------------------------------------ applying operations
+    def apply_state_prep(self, operation, **kwargs) -> bool:
+        is_prep = isinstance(operation, (BasisState, ProductState)) or type(operation).__name__ in ("BasisState",)
+        if kwargs.get("index", 0) > 0 and is_prep:
+            raise DeviceError(f"Operation {type(operation).__name__} cannot be used after other Operations have "
+                              f"already been applied on a {self.name} device.")
+        if isinstance(operation, ProductState):
+            self._state_prep_op = operation
+        elif is_prep:
+            self._state_prep_op = ProductState.from_basis_state(operation)
+        return is_prep
+
+    def convert_op_to_supported(self, op):
+        if isinstance(op, (MatchgateOperation, SingleParticleTransitionMatrixOperation)):
+            return op
+        if isinstance(op, SptmAngleEmbedding):
+            return op
+        if hasattr(op, "to_sptm_operation") or hasattr(op, "single_particle_transition_matrix"):
+            return op
+        try:
+            return MatchgateOperation(np.asarray(op.matrix()), wires=op.wires)
+        except Exception as error:
+            raise DeviceError(
+                f"The {self.name} device can only handle operations that are an instance of MatchgateOperation or "
+                f"SingleParticleTransitionMatrixOperation. The operation {op} is neither and could not be converted "
+                f"to a MatchgateOperation.") from error
+
+    def apply(self, operations, rotations=None, **kwargs) -> None:
+        if not isinstance(operations, Iterable):
+            operations = [operations]
+        self.apply_generator(iter(list(operations)), **kwargs)
+
+    def apply_generator(self, op_iterator: Iterable, **kwargs) -> "NonInteractingFermionicDevice":
+        ops = list(op_iterator)
+        if self._wires is None:
+            all_wires = sorted(set(w for op in ops for w in _wires_tuple(getattr(op, "wires", ()))))
+            assert len(all_wires) > 1, "At least two wires are required for this device."
+            self._wires = tuple(all_wires)
+            self._state_prep_op = ProductState.from_basis_state(np.zeros(self.num_wires, dtype=int), wires=self.wires)
+        n_ops = 0
+        groups = 0
+        container: dict = {}
+        used: set = set()
+        for i, op in enumerate(ops):
+            n_ops = i + 1
+            if type(op).__name__ == "Identity":
+                continue
+            if self.apply_state_prep(op, index=i):
+                continue
+            op = self.convert_op_to_supported(op)
+            expanded = op.decomposition() if isinstance(op, SptmAngleEmbedding) else [op]
+            for e in expanded:
+                self._program.append(e)
+                # emulate the grouping of the chosen contraction strategy for apply_metadata only
+                cs = tuple(self._wire_index(w) for w in e.wires)
+                span = make_wires_continuous(cs)
+                if self.contraction_strategy == "none":
+                    groups += 1
+                elif span in container:
+                    pass
+                elif used & set(span):
+                    groups += 1
+                    container, used = {span: 1}, set(span)
+                else:
+                    container[span] = 1
+                    used |= set(span)
+        if container:
+            groups += 1
+        self._sptm = None
+        self._compiled = None
+        prev_ops = self.apply_metadata.get("n_operations", 0) if kwargs.get("_accumulate") else 0
+        self.apply_metadata["n_operations"] = prev_ops + n_ops
+        self.apply_metadata["n_contracted_operations"] = self.apply_metadata.get("n_contracted_operations", 0) + groups
+        self.apply_metadata["percentage_contracted"] = (
+            100 * (self.apply_metadata["n_operations"] - self.apply_metadata["n_contracted_operations"])
+            / max(self.apply_metadata["n_operations"], 1))
+        if kwargs.get("cache_global_sptm", False):
+            self.apply_metadata["global_sptm"] = self.global_sptm.matrix().cpu().numpy()
+        return self
+
+    # ------------------------------------------------------------------ compilation of the op stream
+    def _op_batch(self, op) -> Optional[int]:
+        return op.batch_size
+
+    def _compile(self):
+        """Split the recorded stream into structured gate segments and dense SPTM factors."""
+        if self._compiled is not None:
+            return self._compiled
+        n = self.num_wires
+        dev = self.torch_device
+        batch = None
+        for op in self._program:
+            b = self._op_batch(op)
+            if b is not None:
+                if batch is not None and b != batch:
+                    raise ValueError(f"Inconsistent batch sizes in the circuit: {batch} and {b}")
+                batch = b
+        self._batched = batch is not None
+        B = batch or 1
+        segments = []
+        gates: List[_ops.GateSpec] = []
+        cols: List[torch.Tensor] = []
+        col_of: dict = {}
+        consts: List[float] = []
+        n_cols = 0
+
+        def param_offset(p, width) -> int:
+            nonlocal n_cols
+            key = id(p)
+            if key in col_of:
+                return col_of[key]
+            t = _as_f64_tensor(p, device=dev).reshape(-1, width)
+            if t.shape[0] == 1 and B > 1:
+                t = t.expand(B, width)
+            cols.append(t)
+            col_of[key] = n_cols
+            n_cols += width
+            return col_of[key]
+
+        def flush():
+            nonlocal gates, cols, col_of, consts, n_cols
+            if gates:
+                key = (n, tuple((g.kind, g.wire0, g.wire1, g.off, g.flags) for g in gates), n_cols, tuple(consts))
+                circ = self._circuit_cache.get(key)
+                if circ is None:
+                    circ = _ops.CompiledCircuit(n, gates, n_cols, consts=np.asarray(consts) if consts else None,
+                                                device=dev)
+                    self._circuit_cache[key] = circ
+                    while len(self._circuit_cache) > 16:
+                        self._circuit_cache.popitem(last=False)
+                else:
+                    self._circuit_cache.move_to_end(key)
+                params = (torch.cat(cols, dim=1) if len(cols) > 1 else cols[0]).contiguous() if cols else \
+                    torch.zeros((B, 0), dtype=torch.float64, device=dev)
+                segments.append(("gates", circ, params))
+            gates, cols, col_of, consts, n_cols = [], [], {}, [], 0
+
+        for op in self._program:
+            idx = tuple(self._wire_index(w) for w in op.wires)
+            if isinstance(op, (CompRotation, _SptmCompRotation)):
+                gates.append(_ops.GateSpec(op.GATE_KIND, idx[0], idx[1], param_offset(op.params, 2)))
+            elif isinstance(op, (CompZX, SptmCompZX)):
+                lo, hi = min(idx), max(idx)
+                gates.append(_ops.GateSpec(_ops.GATE_FSWAP, lo, hi, 0, _ops.FLAG_TRANSPOSE if idx[0] != lo else 0))
+            else:
+                sop = SingleParticleTransitionMatrixOperation.from_operation(op)
+                m = sop.matrix()
+                span = make_wires_continuous(idx)
+                if len(span) == 2 and idx[0] < idx[1]:
+                    mt = _as_f64_tensor(m)
+                    if mt.ndim == 2:
+                        gates.append(_ops.GateSpec(_ops.GATE_BLOCK4_CONST, idx[0], idx[1], len(consts)))
+                        consts.extend(mt.reshape(-1).tolist())
+                    else:
+                        gates.append(_ops.GateSpec(_ops.GATE_BLOCK4_PARAM, idx[0], idx[1], param_offset(m, 16)))
+                else:
+                    flush()
+                    mt = _as_f64_tensor(m, device=dev)
+                    d = 2 * n
+                    if mt.shape[-1] != d:
+                        full = torch.eye(d, dtype=torch.float64, device=dev)
+                        if mt.ndim == 3:
+                            full = full.repeat(mt.shape[0], 1, 1)
+                        o = 2 * span[0]
+                        full[..., o:o + mt.shape[-1], o:o + mt.shape[-1]] = mt
+                        mt = full
+                    segments.append(("dense", mt.contiguous()))
+        flush()
+        self._compiled = (segments, B)
+        return self._compiled
+
+    def _materialize(self) -> torch.Tensor:
+        """Global SPTM (B, d, d) on the device: product of the segments in application order."""
+        if self._sptm is not None:
+            return self._sptm
+        segments, B = self._compile()
+        d = 2 * self.num_wires
+        r = None
+        for seg in segments:
+            rs = _ops.circuit_columns(seg[1], seg[2]) if seg[0] == "gates" else seg[1]
+            r = rs if r is None else _ops.sptm_matmul(r, rs)
+        if r is None:
+            r = torch.eye(d, dtype=torch.float64, device=self.torch_device)[None]
+        if r.ndim == 2:
+            r = r[None]
+        self._sptm = r
+        return r
+
+    def _columns(self, maj: np.ndarray) -> torch.Tensor:
+        """X = R[:, maj] (B, d, m) without forming R when the circuit is a single gate segment."""
+        segments, _ = self._compile()
+        cols = torch.as_tensor(np.asarray(maj, dtype=np.int32), device=self.torch_device)
+        if len(segments) == 1 and segments[0][0] == "gates" and self._sptm is None:
+            return _ops.circuit_columns(segments[0][1], segments[0][2], cols)
+        return self._materialize().index_select(2, cols.long()).contiguous()
+
+    # ------------------------------------------------------------------ SPTM / covariance properties
+    @property
+    def global_sptm(self) -> SingleParticleTransitionMatrixOperation:
+        r = self._materialize()
+        return SingleParticleTransitionMatrixOperation(r if self._batched else r[0], wires=self.wires)
+
+    @global_sptm.setter
+    def global_sptm(self, value) -> None:
+        if isinstance(value, Operation):
+            value = SingleParticleTransitionMatrixOperation.from_operation(value).matrix()
+        t = _as_f64_tensor(value, device=self.torch_device)
+        if t.shape[-1] != 2 * self.num_wires:
+            raise ValueError("global_sptm must be (2N, 2N) or (B, 2N, 2N)")
+        self._program = [SingleParticleTransitionMatrixOperation(t, wires=self.wires)]
+        self._compiled = None
+        self._batched = t.ndim == 3
+        self._sptm = t if t.ndim == 3 else t[None]
+
+    @property
+    def transition_matrix(self):
+        """T = 1/2 (R^T[0::2] + i R^T[1::2]) (utils/__init__.py:352-369) -- kept for API compatibility."""
+        r = self.global_sptm.matrix()
+        rt = r.transpose(-1, -2)
+        return (0.5 * (rt[..., ::2, :] + 1j * rt[..., 1::2, :])).to(self.C_DTYPE)
+
+    def _is_basis_input(self) -> bool:
+        sp = self._state_prep_op
+        return sp.batch_size is None and bool(sp.is_basis_state)
+
+    def _cov_device(self, maj: Optional[np.ndarray] = None) -> torch.Tensor:
+        """(R^T Lambda_0 R)[maj, maj] on the device, (B, m, m)."""
+        n = self.num_wires
+        sp = self._state_prep_op
+        self._compile()
+        if self._is_basis_input():
+            if maj is None:
+                maj = np.arange(2 * n)
+            x = self._columns(maj)
+            bits = torch.as_tensor(sp.basis_state_bits().astype(np.int8), device=self.torch_device)
+            return _ops.cov_basis(x, n, bits)
+        l0 = torch.as_tensor(sp.covariance_matrix, device=self.torch_device)
+        idx = None if maj is None else torch.as_tensor(np.asarray(maj, dtype=np.int32), device=self.torch_device)
+        return _ops.cov_dense(self._materialize(), l0, idx)
+
+    @property
+    def covariance_matrix(self):
+        if not isinstance(self._state_prep_op, ProductState):
+            raise ValueError("Covariance matrix can only be computed for product states.")
+        c = self._cov_device()
+        batched = self._batched or self._state_prep_op.batch_size is not None
+        return self._out(c if batched else c[0])
+
+    def _ext_cov_device(self) -> torch.Tensor:
+        ext0 = torch.as_tensor(self._state_prep_op.extended_covariance_matrix, device=self.torch_device)
+        return _ops.cov_dense(self._materialize(), ext0)
+
+    @property
+    def extended_covariance_matrix(self):
+        c = self._ext_cov_device()
+        batched = self._batched or self._state_prep_op.batch_size is not None
+        return self._out(c if batched else c[0])
+
+    # ------------------------------------------------------------------ probabilities
+    def get_state_probability(self, target_binary_state, wires=None):
+        return self.get_states_probability(target_binary_state, wires)
+
+    def _probs_device(self, target: np.ndarray, wire_idx: np.ndarray) -> torch.Tensor:
+        """(B, Q) probabilities for outcomes ``target`` (Q, k) measured on shared wire indices (k,)."""
+        n = self.num_wires
+        k = target.shape[1]
+        segments, B = self._compile()
+        full_register = k == n and np.array_equal(wire_idx, np.arange(n))
+        if (full_register and target.shape[0] == 1 and self._is_basis_input() and len(segments) == 1
+                and segments[0][0] == "gates" and n <= self.FUSED_MAX_QUBITS):
+            bits = torch.as_tensor(self._state_prep_op.basis_state_bits().astype(np.int8), device=self.torch_device)
+            tgt = torch.as_tensor(target[0].astype(np.int8), device=self.torch_device)
+            return _ops.circuit_expval_projector(segments[0][1], segments[0][2], bits, tgt)[:, None]
+        maj = np.stack([2 * wire_idx, 2 * wire_idx + 1], axis=1).ravel()
+        cov = self._cov_device(maj)
+        outcomes = torch.as_tensor(np.ascontiguousarray(target.astype(np.int8)), device=self.torch_device)
+        return _ops.probs(cov, outcomes)
+
+    def get_states_probability(self, target_binary_states, wires=None, **kwargs):
+        """Scalar / (B,) for one outcome ``(k,)``; ``(Bq,)`` / ``(Bq, B)`` for a batch ``(Bq, k)`` (:742-810)."""
+        if isinstance(target_binary_states, (int, np.integer)):
+            target = np.array([int(c) for c in format(int(target_binary_states), f"0{self.num_wires}b")])
+        elif isinstance(target_binary_states, str):
+            target = np.array([int(c) for c in target_binary_states])
+        else:
+            target = np.asarray(target_binary_states)
+        target = target.astype(int)
+        if np.any((target != 0) & (target != 1)):
+            raise ValueError(f"The binary state must contain only zeros and ones. Currently contains: {np.unique(target)}")
+        is_single = target.ndim == 1
+        if wires is None:
+            wires = self.wires
+        w = np.asarray(_wires_tuple(wires) if not isinstance(wires, np.ndarray) else wires, dtype=object)
+        if is_single:
+            assert len(target) == w.shape[-1], (
+                f"The target binary state must have {w.shape[-1]} elements. Got {len(target)} instead.")
+            target = target[None]
+        if w.ndim == 1:
+            w = np.broadcast_to(w, target.shape)
+        widx = np.vectorize(self._wire_index, otypes=[int])(w) if w.size else np.zeros(w.shape, dtype=int)
+        same = len(target) <= 1 or bool(np.all(widx == widx[0]))
+        if same:
+            p = self._probs_device(target, widx[0])  # (B, Q)
+        else:
+            rows, inverse = np.unique(widx, axis=0, return_inverse=True)
+            parts = {}
+            for r_i, row in enumerate(rows):
+                sel = np.nonzero(inverse.reshape(-1) == r_i)[0]
+                parts[r_i] = (sel, self._probs_device(target[sel], row))
+            nb = next(iter(parts.values()))[1].shape[0]
+            p = torch.empty((nb, len(target)), dtype=torch.float64, device=self.torch_device)
+            for sel, val in parts.values():
+                p[:, torch.as_tensor(sel, device=self.torch_device)] = val
+        p = p.transpose(0, 1)  # (Q, B)
+        batched = self._batched or self._state_prep_op.batch_size is not None
+        if not batched:
+            p = p[:, 0]
+        if is_single:
+            p = p[0]
+        return self._out(p)
+
+    def analytic_probability(self, wires=None):
+        """All 2^k outcomes MSB first, (B, 2^k), divided by the row sum (:430-479)."""
+        if wires is None:
+            wires = self.wires
+        if isinstance(wires, (int, np.integer)):
+            wires = [wires]
+        warr = np.asarray(_wires_tuple(wires) if not isinstance(wires, np.ndarray) else wires, dtype=object)
+        if warr.ndim > 2:
+            raise ValueError(f"The wires must be a 1D or 2D array. Got a {warr.ndim}D array instead.")
+        k = warr.shape[-1]
+        states = self.states_to_binary(np.arange(2 ** k), k)
+        if warr.ndim == 2:
+            return torch.stack([self.analytic_probability(list(row)) for row in warr], dim=-2)
+        widx = np.array([self._wire_index(x) for x in warr], dtype=int)
+        maj = np.stack([2 * widx, 2 * widx + 1], axis=1).ravel()
+        self._compile()
+        cov = self._cov_device(maj)
+        outcomes = torch.as_tensor(np.ascontiguousarray(states.astype(np.int8)), device=self.torch_device)
+        p = _ops.probs(cov, outcomes, normalize=True)
+        batched = self._batched or self._state_prep_op.batch_size is not None
+        return self._out(p if batched else p[0])
+
+    def probability(self, wires=None, shot_range=None, bin_size=None):
+        return self.analytic_probability(wires=wires if wires is not None and len(_wires_tuple(wires)) else self.wires)
+
+    # ------------------------------------------------------------------ expectation values
+    def _expval_pauli_device(self, observable) -> torch.Tensor:
+        n = self.num_wires
+        coeffs, strings = obs_mod.pauli_terms(observable, self.wires)
+        structure = _PauliStructureCache.get(tuple(strings), n)
+        ext = self._ext_cov_device()
+        total = None
+        coeffs_arr = np.asarray(coeffs, dtype=complex)
+        for sector, (index_sets, phases, terms, wick) in structure.items():
+            scalar = np.real(coeffs_arr[terms] * phases * wick).astype(np.float64)
+            feats = _ops.sector_features(ext, torch.as_tensor(index_sets.reshape(len(terms), sector)))
+            total = _ops.rowdot(feats, torch.as_tensor(scalar, device=self.torch_device), out=total)
+        return total
+
+    def exact_expval(self, observable):
+        if isinstance(observable, obs_mod.BatchProjector):
+            return self.get_states_probability(observable.get_states(), observable.get_batch_wires())
+        if _is_projector(observable):
+            return self.get_state_probability(np.asarray(observable.parameters[0]), observable.wires)
+        try:
+            e = self._expval_pauli_device(observable)
+        except TypeError as err:
+            raise DeviceError(
+                f"The expectation value of the observable {observable} with the initial state {self.state_prep_op} "
+                f"cannot be computed on a {self.name} device.") from err
+        batched = self._batched or self._state_prep_op.batch_size is not None
+        return self._out(e if batched else e[0])
+
+    def expval(self, observable, shot_range=None, bin_size=None):
+        return self.exact_expval(observable)
+
+    # ------------------------------------------------------------------ execution
+    def execute_generator(self, op_iterator: Iterable, observable: Optional[Any] = None,
+                          output_type: Optional[str] = None, *, shots: Any = _UNSET, **kwargs):
+        if kwargs.get("reset", False):
+            self.reset()
+        apply = kwargs.get("apply", "auto")
+        if apply == "auto":
+            apply = not self._program and self._sptm is None
+        if apply:
+            self.apply_generator(op_iterator, **kwargs)
+        return self.execute_output(observable=observable, output_type=output_type, shots=shots, **kwargs)
+
+    def execute_output(self, observable: Optional[Any] = None, output_type: Optional[str] = None, *,
+                       shots: Any = _UNSET, **kwargs):
+        if output_type is None:
+            return None
+        if shots is not _UNSET and shots is not None:
+            raise NotImplementedError("Shot-based outputs are outside the B200 hot path.")
+        if output_type == "expval":
+            return self.expval(observable)
+        if output_type == "probs":
+            return self.probability(wires=kwargs.get("wires", None))
+        if output_type in ("samples", "star_state", "*state"):
+            raise NotImplementedError(f"Output type {output_type} (sampling) is outside the B200 hot path.")
+        raise ValueError(f"Output type {output_type} is not supported.")
+
+
+NIFDevice = NonInteractingFermionicDevice

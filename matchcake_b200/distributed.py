@@ -1,0 +1,79 @@
+"""Sharding of the embarrassingly parallel axes over the GPUs of one node (one process per GPU).
+
+The path has exactly one exchange step: an all-gather of equally sized row blocks (NCCL over NVLink on GPUs;
+``gloo`` in the CPU tests).  No reductions, no point-to-point.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+
+def world() -> Tuple[int, int]:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def even_ranges(n: int, parts: int) -> List[Tuple[int, int]]:
+    """Contiguous split of ``range(n)`` into ``parts`` nearly equal pieces (batch axis of expvals / probs)."""
+    base, rem = divmod(n, parts)
+    out, s = [], 0
+    for p in range(parts):
+        e = s + base + (1 if p < rem else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def gram_row_cost(n0: int, n1: int, full: bool = False) -> np.ndarray:
+    """Number of evaluated cells in each Gram row under the reference's triangle rule (gram_matrix.py:191-195)."""
+    i = np.arange(n0)
+    if full:
+        return np.full(n0, n1, dtype=np.int64)
+    if n0 < n1:
+        return np.maximum(n1 - 1 - i, 0).astype(np.int64)
+    return np.minimum(i, n1).astype(np.int64)
+
+
+def balanced_row_ranges(n0: int, n1: int, parts: int, full: bool = False) -> List[Tuple[int, int]]:
+    """Contiguous row blocks with (nearly) equal numbers of evaluated cells."""
+    cost = gram_row_cost(n0, n1, full)
+    csum = np.concatenate([[0], np.cumsum(cost)])
+    total = csum[-1]
+    bounds = [0]
+    for p in range(1, parts):
+        bounds.append(int(np.searchsorted(csum, total * p / parts, side="left")))
+    bounds.append(n0)
+    bounds = np.maximum.accumulate(np.clip(bounds, 0, n0))
+    return [(int(bounds[p]), int(bounds[p + 1])) for p in range(parts)]
+
+
+def all_gather_rows(local: torch.Tensor, ranges: List[Tuple[int, int]], n_rows: int) -> torch.Tensor:
+    """Assemble a (n_rows, ...) tensor from per-rank row blocks ``local`` = rows ranges[rank] with ONE all-gather
+    (blocks are padded to the largest block so that the collective is a plain equal-size all-gather)."""
+    import torch.distributed as dist
+
+    rank, ws = world()
+    if ws == 1:
+        return local
+    max_rows = max(e - s for s, e in ranges)
+    pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    gathered = torch.empty((ws * max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, pad.contiguous())
+    out = torch.empty((n_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r, (s, e) in enumerate(ranges):
+        out[s:e] = gathered[r * max_rows: r * max_rows + (e - s)]
+    return out
+
+
+def sharded_rows(compute_rows: Callable[[int, int], torch.Tensor], ranges: List[Tuple[int, int]], n_rows: int) -> torch.Tensor:
+    """Run ``compute_rows(begin, end)`` for this rank's block and all-gather the result."""
+    rank, ws = world()
+    s, e = ranges[rank]
+    return all_gather_rows(compute_rows(s, e), ranges, n_rows)

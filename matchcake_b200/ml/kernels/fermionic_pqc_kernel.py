@@ -1,0 +1,128 @@
+"""``FermionicPQCKernel`` (mirrors /root/reference/src/matchcake/ml/kernels/fermionic_pqc_kernel.py:28-199)."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from ... import ops as _ops
+from ...operations import SptmAngleEmbedding, SptmCompZX, SingleParticleTransitionMatrixOperation, matchgate_to_sptm_block
+from .nif_kernel import NIFKernel
+
+_ROT_KIND = {"X": _ops.GATE_RXRX, "Y": _ops.GATE_RYRY, "Z": _ops.GATE_RZRZ}
+
+
+def pattern_double(n: int):
+    return [(i, i + 1) for i in range(0, n - 1, 2)]
+
+
+def pattern_double_odd(n: int):
+    return [(i, i + 1) for i in range(1, n - 1, 2)]
+
+
+def _hh_block() -> np.ndarray:
+    h = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+    m = np.zeros((4, 4), dtype=complex)
+    m[0, 0], m[0, 3], m[3, 0], m[3, 3] = h[0, 0], h[0, 1], h[1, 0], h[1, 1]
+    m[1, 1], m[1, 2], m[2, 1], m[2, 2] = h[0, 0], h[0, 1], h[1, 0], h[1, 1]
+    return matchgate_to_sptm_block(m)
+
+
+class FermionicPQCKernel(NIFKernel):
+    DEFAULT_ROTATIONS = "Y,Z"
+    DEFAULT_ENTANGLING_MTH = "fswap"
+    available_entangling_mth = {"fswap", "identity", "hadamard"}
+
+    def __init__(self, *, gram_batch_size: int = NIFKernel.DEFAULT_GRAM_BATCH_SIZE,
+                 random_state: int = NIFKernel.DEFAULT_RANDOM_STATE, alignment: bool = NIFKernel.DEFAULT_ALIGNMENT,
+                 n_qubits: int = NIFKernel.DEFAULT_N_QUBITS, r_dtype: Optional[torch.dtype] = None,
+                 c_dtype: Optional[torch.dtype] = None, rotations: str = DEFAULT_ROTATIONS,
+                 entangling_mth: str = DEFAULT_ENTANGLING_MTH):
+        super().__init__(gram_batch_size=gram_batch_size, random_state=random_state, alignment=alignment,
+                         n_qubits=n_qubits, r_dtype=r_dtype, c_dtype=c_dtype)
+        self.rotations = rotations
+        self.entangling_mth = entangling_mth
+        if self.entangling_mth not in self.available_entangling_mth:
+            raise ValueError(f"Unknown entangling method: {self.entangling_mth}.")
+        self.depth_: Optional[int] = None
+        self.bias_: Optional[np.ndarray] = None
+        self.data_scaling_: Optional[np.ndarray] = None
+        self._circuit = None
+
+    def fit(self, x_train, y_train=None):
+        x_arr = x_train.detach().cpu().numpy() if isinstance(x_train, torch.Tensor) else np.asarray(x_train)
+        n_inputs = int(np.prod(x_arr.shape[1:]))
+        self.bias_ = self.np_rn_gen.random(n_inputs)
+        self.data_scaling_ = np.pi * np.ones(n_inputs)
+        if self.depth_ is None:
+            self.depth_ = int(max(1, np.ceil(x_arr.shape[-1] / self.n_qubits)))
+        self._circuit = None
+        self._covs_train = None
+        super().fit(x_train, y_train)
+        return self
+
+    # ------------------------------------------------------------------ op-object view (API compatibility)
+    def ansatz(self, x):
+        """Yields the same operation stream as the reference (fermionic_pqc_kernel.py:166-199)."""
+        xt = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x, dtype=torch.float64)
+        xt = xt.reshape(len(xt), -1).cpu()
+        xt = torch.as_tensor(self.bias_) + torch.as_tensor(self.data_scaling_) * xt
+        patterns = [pattern_double(self.n_qubits), pattern_double_odd(self.n_qubits)]
+        for layer in range(self.depth_):
+            sub_x = xt[..., layer * self.n_qubits:(layer + 1) * self.n_qubits]
+            yield from SptmAngleEmbedding(sub_x, wires=self.wires, rotations=self.rotations).decomposition()
+            for wires in patterns[layer % 2]:
+                if self.entangling_mth == "fswap":
+                    yield SptmCompZX(wires=wires)
+                elif self.entangling_mth == "hadamard":
+                    yield SingleParticleTransitionMatrixOperation(_hh_block(), wires=wires)
+                elif self.entangling_mth != "identity":
+                    raise ValueError(f"Unknown entangling method: {self.entangling_mth}")
+
+    # ------------------------------------------------------------------ compiled view (what actually runs)
+    def _compiled(self):
+        """The ansatz as ONE device circuit; features are the parameter columns and ``bias + pi * x`` is applied
+        inside the kernel, so no per-gate Python objects and no elementwise pre-pass exist on the hot path."""
+        if self._circuit is not None:
+            return self._circuit
+        nq, f = self.n_qubits, len(self.bias_)
+        gates: List[_ops.GateSpec] = []
+        col_index: List[int] = []   # parameter column -> feature column (f = the constant-zero pad column)
+        consts: List[float] = []
+        patterns = [pattern_double(nq), pattern_double_odd(nq)]
+        for layer in range(self.depth_):
+            cols = list(range(layer * nq, min((layer + 1) * nq, f)))
+            if len(cols) % 2:
+                cols.append(f)  # SptmAngleEmbedding.pad_params: odd feature count -> zero angle
+            for i in range(len(cols) // 2):
+                off = len(col_index)
+                col_index.extend([cols[2 * i], cols[2 * i + 1]])
+                for r in self.rotations.split(","):
+                    gates.append(_ops.GateSpec(_ROT_KIND[r], 2 * i, 2 * i + 1, off))
+            for w0, w1 in patterns[layer % 2]:
+                if self.entangling_mth == "fswap":
+                    gates.append(_ops.GateSpec(_ops.GATE_FSWAP, w0, w1))
+                elif self.entangling_mth == "hadamard":
+                    gates.append(_ops.GateSpec(_ops.GATE_BLOCK4_CONST, w0, w1, len(consts)))
+                    consts.extend(_hh_block().reshape(-1).tolist())
+        idx = np.asarray(col_index, dtype=np.int64)
+        bias = np.concatenate([self.bias_, [0.0]])[idx]
+        scale = np.concatenate([self.data_scaling_, [0.0]])[idx]
+        identity = len(idx) == f and np.array_equal(idx, np.arange(f))
+        circ = _ops.CompiledCircuit(nq, gates, len(idx), scale=scale, bias=bias,
+                                    consts=np.asarray(consts) if consts else None)
+        self._circuit = (circ, None if identity else torch.as_tensor(idx, device="cuda"))
+        return self._circuit
+
+    def _features(self, x) -> torch.Tensor:
+        xt = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x))
+        xt = xt.to(device="cuda", dtype=torch.float64).reshape(len(xt), -1)
+        circ, gather = self._compiled()
+        if gather is not None:
+            xt = torch.cat([xt, torch.zeros((len(xt), 1), dtype=torch.float64, device=xt.device)], dim=1)
+            xt = xt.index_select(1, gather)
+        return xt.contiguous()
+
+    def _x_to_sptm(self, x) -> torch.Tensor:
+        return _ops.circuit_columns(self._compiled()[0], self._features(x))

@@ -1,0 +1,153 @@
+"""``NIFKernel`` -- fermionic kernel Gram builder on the GPU.
+
+Mirrors /root/reference/src/matchcake/ml/kernels/nif_kernel.py:17-264.  The reference evaluates every Gram cell
+as its own circuit (``R = sptm0[i] @ sptm1[j]^T``, complex lookup-table observable, one LU per pair) driven by a
+Python loop over index pairs.  Here:
+
+  1. the ansatz is compiled ONCE into a gate-list circuit and the per-sample SPTMs ``R_i`` come from one kernel
+     launch (``_x_to_sptm``), then the per-sample covariances ``Lambda_i = R_i^T Lambda_0 R_i`` from another;
+  2. every cell is ``K_ij = 2^-N |Pf(Lambda_i + Lambda_j)|`` (identical to
+     ``P(0..0 | R_i R_j^T)``), evaluated by the Gram kernel with the reference's triangle / mirror / unit
+     diagonal rules applied in-kernel;
+  3. with ``torch.distributed`` initialised the rows are sharded over the ranks and assembled by one all-gather.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from ... import distributed as dist_mod
+from ... import ops as _ops
+from ...device import NonInteractingFermionicDevice
+from ...operations import SingleParticleTransitionMatrixOperation
+from .gram_matrix import GramMatrix  # noqa: F401  (re-exported; semantics implemented in-kernel)
+from .kernel import Kernel
+
+
+class NIFKernel(Kernel):
+    DEFAULT_N_QUBITS = 12
+    DEFAULT_R_DTYPE = torch.float32
+    DEFAULT_C_DTYPE = torch.complex64
+
+    def __init__(self, *, gram_batch_size: int = Kernel.DEFAULT_GRAM_BATCH_SIZE,
+                 random_state: int = Kernel.DEFAULT_RANDOM_STATE, alignment: bool = Kernel.DEFAULT_ALIGNMENT,
+                 n_qubits: int = DEFAULT_N_QUBITS, r_dtype: Optional[torch.dtype] = None,
+                 c_dtype: Optional[torch.dtype] = None):
+        super().__init__(gram_batch_size=gram_batch_size, random_state=random_state, alignment=alignment)
+        self._r_dtype = r_dtype or self.DEFAULT_R_DTYPE
+        self._c_dtype = c_dtype or self.DEFAULT_C_DTYPE
+        self._n_qubits = int(n_qubits)
+        self._q_device = None
+        self._covs_train = None
+        #: store the Gram in float32 like the reference's GramMatrix (gram_matrix.py:38-47); False keeps float64
+        self.float32_gram = True
+
+    # sklearn's get_params reads attributes named like the __init__ arguments
+    @property
+    def n_qubits(self) -> int:
+        return self._n_qubits
+
+    @n_qubits.setter
+    def n_qubits(self, value: int):
+        self._n_qubits = int(value)
+        self._q_device = None
+
+    @property
+    def r_dtype(self):
+        return self._r_dtype
+
+    @property
+    def c_dtype(self):
+        return self._c_dtype
+
+    @property
+    def R_DTYPE(self):
+        return self._r_dtype
+
+    @property
+    def C_DTYPE(self):
+        return self._c_dtype
+
+    @property
+    def q_device(self) -> NonInteractingFermionicDevice:
+        if self._q_device is None:
+            self._q_device = NonInteractingFermionicDevice(self._n_qubits, r_dtype=self._r_dtype,
+                                                           c_dtype=self._c_dtype, output_device="cuda")
+        return self._q_device
+
+    @property
+    def wires(self):
+        return tuple(range(self._n_qubits))
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x0, x1=None, **kwargs) -> torch.Tensor:
+        if x1 is None:
+            x1 = x0
+        return self.compute_similarities(x0, x1, **kwargs)
+
+    def ansatz(self, x):
+        raise NotImplementedError
+
+    def circuit(self, sptm0, sptm1):
+        """The per-pair circuit of the reference (nif_kernel.py:159-177), kept for API compatibility."""
+        yield SingleParticleTransitionMatrixOperation(sptm0, wires=self.wires)
+        yield SingleParticleTransitionMatrixOperation(sptm1, wires=self.wires).adjoint()
+
+    def _x_to_sptm(self, x) -> torch.Tensor:
+        """(n_samples, 2N, 2N) SPTMs; generic route through the device for subclasses that only define
+        ``ansatz`` (FermionicPQCKernel overrides this with a compiled circuit)."""
+        dev = self.q_device
+        dev.execute_generator(self.ansatz(x), reset=True)
+        r = dev._materialize()
+        return r.expand(len(x), -1, -1) if r.shape[0] == 1 else r
+
+    def _x_to_cov(self, x) -> torch.Tensor:
+        """Per-sample covariance Lambda_i = R_i^T Lambda_0 R_i for the |0..0> input (n_samples, 2N, 2N)."""
+        return _ops.cov_basis(self._x_to_sptm(x), self._n_qubits)
+
+    @property
+    def sptms_train(self) -> torch.Tensor:
+        return self._x_to_sptm(self.x_train_)
+
+    @property
+    def covs_train(self) -> torch.Tensor:
+        if self._covs_train is None or self._covs_train[0] is not self.x_train_:
+            self._covs_train = (self.x_train_, self._x_to_cov(self.x_train_))
+        return self._covs_train[1]
+
+    def compute_similarities(self, x0, x1, **kwargs) -> torch.Tensor:
+        same = x1 is x0
+        cov0 = self._x_to_cov(x0)
+        if kwargs.get("x1_train", False):
+            cov1 = self.covs_train
+        else:
+            cov1 = cov0 if same else self._x_to_cov(x1)
+        k = self.gram_from_covariances(cov0, cov1, full=kwargs.get("full_rectangle", False))
+        if self.float32_gram:
+            k = k.to(torch.float32)
+        return k.to(self.R_DTYPE)
+
+    def gram_from_covariances(self, cov0: torch.Tensor, cov1: torch.Tensor, full: bool = False) -> torch.Tensor:
+        n0, n1 = cov0.shape[0], cov1.shape[0]
+        scale = 2.0 ** (-self._n_qubits)
+        rank, ws = dist_mod.world()
+        if ws == 1:
+            return _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE)
+        ranges = dist_mod.balanced_row_ranges(n0, n1, ws, full=full)
+
+        def rows(s, e):
+            out = torch.zeros((n0, n1), dtype=torch.float64, device=cov0.device)
+            _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_TRIANGLE, row_range=(s, e), out=out)
+            return out[s:e]
+
+        k = dist_mod.sharded_rows(rows, ranges, n0)
+        return k if full else _ops.gram_symmetrize(k)
+
+    def _compute_similarities_func(self, indices, sptm0, sptm1, p_bar=None):
+        """Expectation values for explicit index pairs (nif_kernel.py:210-221), float64, on the GPU."""
+        idx = torch.as_tensor(np.asarray(indices), device=sptm0.device)
+        c0 = _ops.cov_basis(sptm0[idx[:, 0]].contiguous(), self._n_qubits)
+        c1 = _ops.cov_basis(sptm1[idx[:, 1]].contiguous(), self._n_qubits)
+        return _ops.pfaffian(c0 + c1, signed=False, scale=2.0 ** (-self._n_qubits))
