@@ -1,0 +1,37 @@
+"""Small single-GPU targets for ncu: python scripts/profile_target.py {c2|gram|c4|pf} [size]"""
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from bench import readme_gate_specs
+from matchcake_b200 import ops as mops
+
+what = sys.argv[1]
+size = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+dev = torch.device("cuda")
+rng = np.random.default_rng(0)
+if what == "c2":
+    n, B = 16, size or 65536
+    circ = mops.CompiledCircuit(n, readme_gate_specs(n, mops), 2)
+    p = torch.as_tensor(rng.uniform(0, 2 * np.pi, (B, 2))).to(dev)
+    for _ in range(3):
+        out = mops.circuit_expval_projector(circ, p)
+elif what == "gram":
+    from matchcake_b200.ml.kernels import FermionicPQCKernel
+
+    n, ns = 32, size or 1024
+    x = rng.random((ns, 2 * n))
+    k = FermionicPQCKernel(n_qubits=n, rotations="X,Z", r_dtype=torch.float64, c_dtype=torch.complex128)
+    k.fit(x)
+    for _ in range(2):
+        out = k(torch.as_tensor(x).to(dev))
+elif what == "pf":
+    m = size or 64
+    a = torch.randn(20000, m, m, dtype=torch.float64, device=dev)
+    a = a - a.transpose(1, 2)
+    for _ in range(3):
+        out = mops.pfaffian(a)
+torch.cuda.synchronize()
+print("done", float(out.sum()))
