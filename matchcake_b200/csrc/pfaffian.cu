@@ -10,6 +10,7 @@
 //   Gram    cov0[i] + cov1[j]                 nif_kernel.py:210-221 via SURVEY.md A.5
 #include "common.cuh"
 #include "pfaffian_dev.cuh"
+#include "tiles_api.cuh"
 
 namespace mcb200 {
 
@@ -287,6 +288,7 @@ extern "C" int mcb200_pfaffian(const double* A, int64_t n, int32_t m, int32_t mo
     return check_launch("fill_kernel");
   }
   if (A == nullptr) return set_error("pfaffian: A is NULL");
+  if (m <= kTilesMaxM) return tiles_pfaffian_plain(A, n, m, mode, scale, out, st);
   PlainLoader ld{A, out, scale, mode};
   return launch_pfaffian(ld, n, m, (double*)workspace, st, "pfaffian_kernel");
 }
@@ -299,8 +301,12 @@ extern "C" int mcb200_probs(const double* cov, const int8_t* outcomes, int64_t B
   if (2 * k > kWarpKernelMaxM) return set_error("probs: k=%d measured wires exceed the fused limit of %d", k,
                                                  kWarpKernelMaxM / 2);
   cudaStream_t st = as_stream(stream);
-  ProbsLoader ld{cov, outcomes, out, Q, k};
-  if (int rc = launch_pfaffian(ld, (long long)B * Q, 2 * k, nullptr, st, "probs_kernel")) return rc;
+  if (2 * k <= kTilesMaxM) {
+    if (int rc = tiles_pfaffian_probs(cov, outcomes, B, Q, k, out, st)) return rc;
+  } else {
+    ProbsLoader ld{cov, outcomes, out, Q, k};
+    if (int rc = launch_pfaffian(ld, (long long)B * Q, 2 * k, nullptr, st, "probs_kernel")) return rc;
+  }
   if (normalize) {
     normalize_rows_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(out, B, Q);
     return check_launch("normalize_rows_kernel");
@@ -325,6 +331,7 @@ extern "C" int mcb200_sector_features(const double* cov, int64_t B, int32_t D, c
     return check_launch("sector_gather2_kernel");
   }
   if (s > kWarpKernelMaxM) return set_error("sector_features: sector size %d > %d", s, kWarpKernelMaxM);
+  if (s <= kTilesMaxM) return tiles_pfaffian_sector(cov, B, D, index_sets, T, s, feats, st);
   SectorLoader ld{cov, index_sets, feats, D, T};
   return launch_pfaffian(ld, n, s, nullptr, st, "sector_pfaffian_kernel");
 }
@@ -339,6 +346,7 @@ extern "C" int mcb200_rowdot(const double* feats, const double* coeffs, int64_t 
 }
 
 extern "C" int64_t mcb200_gram_workspace_bytes(int64_t n0, int64_t n1, int32_t d) {
+  if (d <= kTilesMaxM) return tiles_gram_workspace_bytes(n0, n1, d);
   if (d <= kWarpKernelMaxM) return 0;
   return (int64_t)kBlockGlobalCtas * d * (d + 1) * (int64_t)sizeof(double);
 }
@@ -357,7 +365,9 @@ extern "C" int mcb200_gram(const double* cov0, const double* cov1, int64_t n0, i
   if (cov0 == nullptr || cov1 == nullptr || K == nullptr) return set_error("gram: NULL pointer");
   cudaStream_t st = as_stream(stream);
   GramArgs g{cov0, cov1, n0, n1, d, row_begin, mode, scale, K, ldk};
-  if (d <= kWarpKernelMaxM) {
+  if (d <= kTilesMaxM) {
+    if (int rc = tiles_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st)) return rc;
+  } else if (d <= kWarpKernelMaxM) {
     const size_t per_warp = (size_t)d * (d + 1) * sizeof(double);
     int warps = (int)((200 * 1024) / per_warp);
     if (warps > 8) warps = 8;

@@ -1,0 +1,250 @@
+// K3 fast path for m <= 64: warp-per-matrix Pfaffians with the matrix held as DMMA accumulator fragments
+// (pfaffian_tiles.cuh).  Entry points are internal (declared in tiles_api.cuh) and are dispatched to from the
+// public C ABI in pfaffian.cu.
+#include "common.cuh"
+#include "pfaffian_tiles.cuh"
+#include "tiles_api.cuh"
+
+namespace mcb200 {
+
+// ------------------------------------------------------------------------------------------- fragment sources
+// A source returns A[i][j] of matrix `item` for arbitrary 0 <= i, j < 8*MT (0 outside the real matrix).
+struct PlainSrc {
+  const double* A;
+  int m;
+  __device__ __forceinline__ double at(long long item, int i, int j) const {
+    if (i >= m || j >= m || i == j) return 0.0;
+    const double* a = A + item * (long long)m * m;
+    return i < j ? a[i * m + j] : -a[j * m + i];  // only the strict upper triangle is trusted
+  }
+};
+
+struct ProbsSrc {
+  const double* cov;
+  const int8_t* outcomes;
+  int Q, k, m;
+  __device__ __forceinline__ double at(long long item, int i, int j) const {
+    if (i >= m || j >= m || i == j) return 0.0;
+    const long long b = item / Q;
+    const int q = (int)(item - b * Q);
+    const double* a = cov + b * (long long)m * m;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    double v = a[lo * m + hi];
+    if ((lo & 1) == 0 && hi == lo + 1) v += outcomes[(long long)q * k + (lo >> 1)] ? 1.0 : -1.0;
+    return i < j ? v : -v;
+  }
+};
+
+struct SectorSrc {
+  const double* cov;
+  const int32_t* index_sets;
+  int D, T, m;
+  __device__ __forceinline__ double at(long long item, int i, int j) const {
+    if (i >= m || j >= m || i == j) return 0.0;
+    const long long b = item / T;
+    const int t = (int)(item - b * T);
+    const int32_t* idx = index_sets + (long long)t * m;
+    const double* a = cov + b * (long long)D * D;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    const double v = a[(long long)idx[lo] * D + idx[hi]];
+    return i < j ? v : -v;
+  }
+};
+
+template <int MT, class Src>
+__device__ __forceinline__ void load_fragments(const Src& src, long long item, double (&c)[Tiles<MT>::NT][2]) {
+  const int lane = lane_id(), gr = lane >> 2, tg = lane & 3;
+#pragma unroll
+  for (int ti = 0; ti < MT; ++ti)
+#pragma unroll
+    for (int tj = ti; tj < MT; ++tj) {
+      c[Tiles<MT>::idx(ti, tj)][0] = src.at(item, 8 * ti + gr, 8 * tj + 2 * tg);
+      c[Tiles<MT>::idx(ti, tj)][1] = src.at(item, 8 * ti + gr, 8 * tj + 2 * tg + 1);
+    }
+}
+
+template <int MT, class Src>
+__global__ void __launch_bounds__(128) pfaffian_tiles_kernel(Src src, long long n_items, int m, int out_mode,
+                                                             double scale, double* out) {
+  extern __shared__ double smem[];
+  double* scratch = smem + (size_t)warp_id() * Tiles<MT>::kScratch;
+  const int warps = blockDim.x >> 5;
+  for (long long item = (long long)blockIdx.x * warps + warp_id(); item < n_items;
+       item += (long long)gridDim.x * warps) {
+    double c[Tiles<MT>::NT][2];
+    load_fragments<MT>(src, item, c);
+    double pf = warp_pfaffian_tiles<MT>(c, m, scratch);
+    if (lane_id() == 0) out[item] = scale * (out_mode == MCB200_PF_SIGNED ? pf : fabs(pf));
+    __syncwarp();
+  }
+}
+
+template <class Src>
+static int launch_tiles(const Src& src, long long n_items, int m, int out_mode, double scale, double* out,
+                        cudaStream_t st, const char* what) {
+  if (n_items == 0) return 0;
+  const int warps = 4;
+  long long blocks = (n_items + warps - 1) / warps;
+  const long long cap = 16LL * kNumSMs;
+  if (blocks > cap) blocks = cap;
+  auto go = [&](auto kernel, int mt) -> int {
+    const size_t smem = (size_t)warps * 6 * 8 * mt * sizeof(double);
+    kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(src, n_items, m, out_mode, scale, out);
+    return check_launch(what);
+  };
+  if (m <= 8) return go(pfaffian_tiles_kernel<1, Src>, 1);
+  if (m <= 16) return go(pfaffian_tiles_kernel<2, Src>, 2);
+  if (m <= 24) return go(pfaffian_tiles_kernel<3, Src>, 3);
+  if (m <= 32) return go(pfaffian_tiles_kernel<4, Src>, 4);
+  if (m <= 48) return go(pfaffian_tiles_kernel<6, Src>, 6);
+  return go(pfaffian_tiles_kernel<8, Src>, 8);
+}
+
+int tiles_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out, cudaStream_t st) {
+  PlainSrc s{A, m};
+  return launch_tiles(s, n, m, mode, scale, out, st, "pfaffian_tiles_kernel");
+}
+
+int tiles_pfaffian_probs(const double* cov, const int8_t* outcomes, long long B, int Q, int k, double* out,
+                         cudaStream_t st) {
+  ProbsSrc s{cov, outcomes, Q, k, 2 * k};
+  return launch_tiles(s, B * Q, 2 * k, MCB200_PF_ABS, ldexp(1.0, -k), out, st, "probs_tiles_kernel");
+}
+
+int tiles_pfaffian_sector(const double* cov, long long B, int D, const int32_t* index_sets, int T, int s,
+                          double* feats, cudaStream_t st) {
+  SectorSrc src{cov, index_sets, D, T, s};
+  return launch_tiles(src, B * T, s, MCB200_PF_SIGNED, 1.0, feats, st, "sector_tiles_kernel");
+}
+
+// ------------------------------------------------------------------------------------------- Gram
+// Packed covariance: for every sample the NT upper tiles in fragment order, [sample][tile][lane] as double2
+// (c0, c1), zero beyond the real matrix -> a warp reads one tile as 32 coalesced 16-byte loads.
+template <int MT>
+__global__ void pack_tiles_kernel(const double* __restrict__ cov, long long n, int m, double2* __restrict__ packed) {
+  constexpr int NT = Tiles<MT>::NT;
+  const long long total = n * NT * 32;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int lane = (int)(e & 31);
+    const long long rest = e >> 5;
+    const int t = (int)(rest % NT);
+    const long long smp = rest / NT;
+    // invert t -> (ti, tj)
+    int ti = 0, base = 0;
+    while (t >= base + (MT - ti)) {
+      base += MT - ti;
+      ++ti;
+    }
+    const int tj = ti + (t - base);
+    const int i = 8 * ti + (lane >> 2), j = 8 * tj + 2 * (lane & 3);
+    const double* a = cov + smp * (long long)m * m;
+    auto at = [&](int r, int cc) -> double {
+      if (r >= m || cc >= m || r == cc) return 0.0;
+      return r < cc ? a[r * m + cc] : -a[cc * m + r];
+    };
+    packed[e] = make_double2(at(i, j), at(i, j + 1));
+  }
+}
+
+struct GramTileArgs {
+  const double2* p0;
+  const double2* p1;
+  long long n0, n1;
+  int m;
+  long long row_begin, row_end;
+  int mode;
+  double scale;
+  double* K;
+  long long ldk;
+};
+
+// One warp per (i, j) cell.  A block of TI x TJ warps walks (row-block, column-block) tiles so that the fragments
+// of the TI + TJ covariances it touches stay in L1.
+template <int MT, int TI, int TJ>
+__global__ void __launch_bounds__(32 * TI * TJ, 1) gram_tiles_kernel(GramTileArgs g) {
+  constexpr int NT = Tiles<MT>::NT;
+  extern __shared__ double smem[];
+  double* scratch = smem + (size_t)warp_id() * Tiles<MT>::kScratch;
+  const int lane = lane_id();
+  const int wi = warp_id() / TJ, wj = warp_id() % TJ;
+  const long long rows = g.row_end - g.row_begin;
+  const long long rb_n = (rows + TI - 1) / TI, cb_n = (g.n1 + TJ - 1) / TJ;
+  const bool upper = g.n0 < g.n1;  // reference rule: evaluate j > i, else i > j (gram_matrix.py:191-195)
+  for (long long t = blockIdx.x; t < rb_n * cb_n; t += gridDim.x) {
+    const long long rb = t / cb_n, cb = t - rb * cb_n;
+    const long long i_lo = g.row_begin + rb * TI, j_lo = cb * TJ;
+    if (g.mode != MCB200_GRAM_FULL) {  // skip tiles that hold no evaluated cell (uniform over the block)
+      if (!upper && j_lo >= i_lo + TI - 1 + 1) continue;      // all j >= i
+      if (upper && j_lo + TJ - 1 <= i_lo) continue;           // all j <= i
+    }
+    const long long i = i_lo + wi, j = j_lo + wj;
+    bool on = i < g.row_end && j < g.n1;
+    if (g.mode != MCB200_GRAM_FULL) on = on && (upper ? (j > i) : (i > j));
+    if (!on) continue;
+    const double2* a = g.p0 + i * (long long)(NT * 32) + lane;
+    const double2* b = g.p1 + j * (long long)(NT * 32) + lane;
+    double c[NT][2];
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+      const double2 x = __ldg(a + q * 32), y = __ldg(b + q * 32);
+      c[q][0] = x.x + y.x;
+      c[q][1] = x.y + y.y;
+    }
+    const double pf = warp_pfaffian_tiles<MT>(c, g.m, scratch);
+    if (lane == 0) {
+      const double v = g.scale * fabs(pf);
+      g.K[i * g.ldk + j] = v;
+      if (g.mode == MCB200_GRAM_REFERENCE && j < g.n0 && i < g.n1) g.K[j * g.ldk + i] = v;  // gram_matrix.py:139-143
+    }
+    __syncwarp();
+  }
+}
+
+long long tiles_gram_workspace_bytes(long long n0, long long n1, int d) {
+  if (d > 64) return 0;
+  const int mt = d <= 8 ? 1 : d <= 16 ? 2 : d <= 24 ? 3 : d <= 32 ? 4 : d <= 48 ? 6 : 8;
+  return (n0 + n1) * (long long)(mt * (mt + 1) / 2) * 32 * (long long)sizeof(double2);
+}
+
+template <int MT>
+static int gram_tiles_launch(const double* cov0, const double* cov1, long long n0, long long n1, int d,
+                             long long row_begin, long long row_end, int mode, double scale, double* K,
+                             long long ldk, void* workspace, cudaStream_t st) {
+  constexpr int NT = Tiles<MT>::NT;
+  double2* p0 = (double2*)workspace;
+  double2* p1 = p0 + n0 * (long long)NT * 32;
+  const bool same = (cov0 == cov1 && n0 == n1);
+  auto pack = [&](const double* cov, long long n, double2* dst) -> int {
+    long long blocks = (n * NT * 32 + 255) / 256;
+    if (blocks > 32LL * kNumSMs) blocks = 32LL * kNumSMs;
+    pack_tiles_kernel<MT><<<(unsigned)blocks, 256, 0, st>>>(cov, n, d, dst);
+    return check_launch("pack_tiles_kernel");
+  };
+  if (int rc = pack(cov0, n0, p0)) return rc;
+  if (same) p1 = p0;
+  else if (int rc = pack(cov1, n1, p1)) return rc;
+  GramTileArgs g{p0, p1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk};
+  constexpr int TI = 2, TJ = (MT >= 8) ? 4 : 8;
+  const size_t smem = (size_t)TI * TJ * Tiles<MT>::kScratch * sizeof(double);
+  const long long rows = row_end - row_begin;
+  const long long tiles = ((rows + TI - 1) / TI) * ((n1 + TJ - 1) / TJ);
+  const int per_sm = (MT >= 8) ? 1 : 2;
+  long long blocks = tiles < (long long)per_sm * kNumSMs ? tiles : (long long)per_sm * kNumSMs;
+  gram_tiles_kernel<MT, TI, TJ><<<(unsigned)blocks, 32 * TI * TJ, smem, st>>>(g);
+  return check_launch("gram_tiles_kernel");
+}
+
+int tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
+               long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,
+               cudaStream_t st) {
+  if (workspace == nullptr) return set_error("gram: workspace is NULL (see mcb200_gram_workspace_bytes)");
+  if (d <= 8) return gram_tiles_launch<1>(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st);
+  if (d <= 16) return gram_tiles_launch<2>(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st);
+  if (d <= 24) return gram_tiles_launch<3>(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st);
+  if (d <= 32) return gram_tiles_launch<4>(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st);
+  if (d <= 48) return gram_tiles_launch<6>(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st);
+  return gram_tiles_launch<8>(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st);
+}
+
+}  // namespace mcb200

@@ -1,0 +1,17 @@
+// Internal entry points of the register-tile (DMMA) Pfaffian path, m <= 64 (pfaffian_tiles.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mcb200 {
+constexpr int kTilesMaxM = 64;
+int tiles_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out, cudaStream_t st);
+int tiles_pfaffian_probs(const double* cov, const int8_t* outcomes, long long B, int Q, int k, double* out,
+                         cudaStream_t st);
+int tiles_pfaffian_sector(const double* cov, long long B, int D, const int32_t* index_sets, int T, int s,
+                          double* feats, cudaStream_t st);
+long long tiles_gram_workspace_bytes(long long n0, long long n1, int d);
+int tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
+               long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,
+               cudaStream_t st);
+}  // namespace mcb200
