@@ -1,0 +1,256 @@
+// Fused projector expectation value, one WARP per circuit instance (2N <= 64):
+//   gate list -> X = R (d x d, shared memory, lane = column) -> Lambda = X^T Lambda_0 X as DMMA accumulator
+//   fragments -> + Lambda_y -> register-tile Pfaffian (pfaffian_tiles.cuh) -> 2^-N |Pf|.
+// Nothing but the parameter row (16 B for config C2) is read from HBM and 8 B are written per instance.
+//
+//  * Gates are applied in reverse application order from the left (see circuit.cu); consecutive gates on the
+//    same wire pair are applied while the four rows are still in registers.
+//  * fSWAPs (adjacent or long range) move no data: they permute a logical->physical row table.
+//  * The conjugation with a basis-state Lambda_0 is a skew rank-2 update per wire,
+//        Lambda += s_k (e_k^T o_k - o_k^T e_k),  e_k = X[2k,:], o_k = X[2k+1,:], s_k = -(-1)^{bit_k},
+//    i.e. one DMMA (K = 4) per wire PAIR and upper tile: A-fragment columns (s e_k, -s o_k, s' e_k', -s' o_k'),
+//    B-fragment rows (o_k; e_k; o_k'; e_k').  The result lands directly in the Pfaffian's register layout.
+// Replaces the QNode execution path of SURVEY.md section 3.1 (devices/nif_device.py:562 -> :281 -> :506 -> :742,
+// lookup_table_strategy.py:19-71, utils/_pfaffian.py:78-119).
+#include "common.cuh"
+#include "pfaffian_tiles.cuh"
+#include "tiles_api.cuh"
+
+namespace mcb200 {
+
+struct WarpCircuit {
+  const mcb200_gate_t* gates;
+  int n_gates, n_qubits, n_param_cols;
+  const double* scale;
+  const double* bias;
+  const double* consts;
+};
+
+__device__ __forceinline__ double wc_angle(const WarpCircuit& c, const double* prow, int col) {
+  double x = prow[col];
+  if (c.scale != nullptr) x = c.bias[col] + c.scale[col] * x;
+  return x;
+}
+
+// {c1, t1, c2, t2} of a rotation gate: two Givens pairs new_i = c x_i + t x_j, new_j = c x_j - t x_i
+__device__ __forceinline__ void wc_rotation_coef(const WarpCircuit& c, const mcb200_gate_t& g, const double* prow,
+                                                 double* out) {
+  const double p0 = wc_angle(c, prow, g.off), p1 = wc_angle(c, prow, g.off + 1);
+  double a1, a2, s, co;
+  if (g.kind == MCB200_GATE_RXRX) {          // pairs (0,3): cos/-sin(phi-theta); (1,2): cos/sin(phi+theta)
+    a1 = p1 / 2 - p0 / 2;
+    a2 = p1 / 2 + p0 / 2;
+    sincos(a1, &s, &co);
+    out[0] = co;
+    out[1] = -s;
+  } else if (g.kind == MCB200_GATE_RYRY) {   // pairs (0,2): cos/-sin((t+p)/2); (1,3): cos/sin((t-p)/2)
+    a1 = (p0 + p1) / 2;
+    a2 = (p0 - p1) / 2;
+    sincos(a1, &s, &co);
+    out[0] = co;
+    out[1] = -s;
+  } else {                                   // RZRZ pairs (0,1): cos/sin((t+p)/2); (2,3): cos/sin((t-p)/2)
+    a1 = (p0 + p1) / 2;
+    a2 = (p0 - p1) / 2;
+    sincos(a1, &s, &co);
+    out[0] = co;
+    out[1] = s;
+  }
+  sincos(a2, &s, &co);
+  out[2] = co;
+  out[3] = s;
+}
+
+template <int MT>
+__global__ void __launch_bounds__(128) expval_warp_kernel(WarpCircuit wc, const double* __restrict__ params,
+                                                          long long B, const int8_t* init_bits,
+                                                          const int8_t* target_bits, int gates_in_smem,
+                                                          double* __restrict__ out) {
+  using T = Tiles<MT>;
+  constexpr int M = T::M;
+  constexpr int LDX = M + 4;                 // = 4 mod 16 (in doubles) for M = 16, 32, 48, 64: spreads fragment reads
+  constexpr int H = (M + 31) / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = wc.n_qubits, d = 2 * n;
+  const int warps = blockDim.x >> 5, w = warp_id(), lane = lane_id(), gr = lane >> 2, tg = lane & 3;
+  // shared layout: [gates (block)] [per warp: X (64 x LDX... d rows) | coef 32x4 | scratch | phys]
+  mcb200_gate_t* sg = reinterpret_cast<mcb200_gate_t*>(smem_raw);
+  const size_t gate_bytes = gates_in_smem ? (((size_t)wc.n_gates * sizeof(mcb200_gate_t) + 15) & ~(size_t)15) : 0;
+  const size_t per_warp = ((((size_t)d * LDX + 128 + T::kScratch) * sizeof(double) + 64) + 15) & ~(size_t)15;
+  unsigned char* wbase = smem_raw + gate_bytes + (size_t)w * per_warp;
+  double* X = reinterpret_cast<double*>(wbase);
+  double* coef = X + (size_t)d * LDX;
+  double* scratch = coef + 128;
+  unsigned char* phys = reinterpret_cast<unsigned char*>(scratch + T::kScratch);
+  if (gates_in_smem) {
+    for (int i = threadIdx.x; i < wc.n_gates * 6; i += blockDim.x)
+      reinterpret_cast<int32_t*>(sg)[i] = reinterpret_cast<const int32_t*>(wc.gates)[i];
+    __syncthreads();
+  }
+  const mcb200_gate_t* gl = gates_in_smem ? sg : wc.gates;
+
+  for (long long b = (long long)blockIdx.x * warps + w; b < B; b += (long long)gridDim.x * warps) {
+    const double* prow = params + b * wc.n_param_cols;
+    // X = I (lane owns column(s) lane, lane+32), phys = identity
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      const int col = lane + 32 * h;
+      if (col < M)
+        for (int r = 0; r < d; ++r) X[r * LDX + col] = (r == col) ? 1.0 : 0.0;
+    }
+    for (int r = lane; r < d; r += 32) phys[r] = (unsigned char)r;
+    __syncwarp();
+    // gates in reverse application order, 32 at a time
+    for (int top = wc.n_gates - 1; top >= 0; top -= 32) {
+      {
+        const int gi = top - lane;
+        if (gi >= 0) {
+          const mcb200_gate_t g = gl[gi];
+          if (g.kind <= MCB200_GATE_RZRZ) wc_rotation_coef(wc, g, prow, coef + 4 * lane);
+        }
+      }
+      __syncwarp();
+      const int cnt = top + 1 < 32 ? top + 1 : 32;
+      int q = 0;
+      while (q < cnt) {
+        const mcb200_gate_t g = gl[top - q];
+        if (g.kind == MCB200_GATE_FSWAP) {
+          // rows of the block: s = 2 (w1 - w0 + 1); new[0:2] = old[s-2:s], new[i] = old[i-2]  (transpose: inverse)
+          const int r0 = 2 * g.wire0, s = 2 * (g.wire1 - g.wire0 + 1);
+          // cyclic shift of the logical->physical table over [r0, r0+s)
+          unsigned char v0 = 0, v1 = 0;
+          const bool fwd = !(g.flags & MCB200_GATE_FLAG_TRANSPOSE);
+          const int i0 = lane, i1 = lane + 32;
+          if (i0 < s) v0 = phys[r0 + (fwd ? (i0 + s - 2) % s : (i0 + 2) % s)];
+          if (i1 < s) v1 = phys[r0 + (fwd ? (i1 + s - 2) % s : (i1 + 2) % s)];
+          __syncwarp();
+          if (i0 < s) phys[r0 + i0] = v0;
+          if (i1 < s) phys[r0 + i1] = v1;
+          __syncwarp();
+          ++q;
+          continue;
+        }
+        const int r0 = 2 * g.wire0;
+        const int p0 = phys[r0], p1 = phys[r0 + 1], p2 = phys[r0 + 2], p3 = phys[r0 + 3];
+        // how many consecutive gates (going down the list) act on the same wire pair and are not fSWAPs
+        int run = 1;
+        while (q + run < cnt) {
+          const mcb200_gate_t g2 = gl[top - q - run];
+          if (g2.kind == MCB200_GATE_FSWAP || g2.wire0 != g.wire0) break;
+          ++run;
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const int col = lane + 32 * h;
+          if (col < M) {
+            double x0 = X[p0 * LDX + col], x1 = X[p1 * LDX + col], x2 = X[p2 * LDX + col], x3 = X[p3 * LDX + col];
+            for (int u = 0; u < run; ++u) {
+              const mcb200_gate_t gu = gl[top - q - u];
+              if (gu.kind <= MCB200_GATE_RZRZ) {
+                const double4 cf = *reinterpret_cast<const double4*>(coef + 4 * (q + u));
+                double y0, y1, y2, y3;
+                if (gu.kind == MCB200_GATE_RXRX) {        // pairs (0,3), (1,2)
+                  y0 = cf.x * x0 + cf.y * x3;  y3 = cf.x * x3 - cf.y * x0;
+                  y1 = cf.z * x1 + cf.w * x2;  y2 = cf.z * x2 - cf.w * x1;
+                } else if (gu.kind == MCB200_GATE_RYRY) { // pairs (0,2), (1,3)
+                  y0 = cf.x * x0 + cf.y * x2;  y2 = cf.x * x2 - cf.y * x0;
+                  y1 = cf.z * x1 + cf.w * x3;  y3 = cf.z * x3 - cf.w * x1;
+                } else {                                   // pairs (0,1), (2,3)
+                  y0 = cf.x * x0 + cf.y * x1;  y1 = cf.x * x1 - cf.y * x0;
+                  y2 = cf.z * x2 + cf.w * x3;  y3 = cf.z * x3 - cf.w * x2;
+                }
+                x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+              } else {  // explicit 4x4 block
+                const double* m4 = (gu.kind == MCB200_GATE_BLOCK4_CONST) ? wc.consts + gu.off : prow + gu.off;
+                const bool tr = gu.flags & MCB200_GATE_FLAG_TRANSPOSE;
+                double y[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+                  y[a] = (tr ? m4[a] : m4[4 * a]) * x0 + (tr ? m4[4 + a] : m4[4 * a + 1]) * x1 +
+                         (tr ? m4[8 + a] : m4[4 * a + 2]) * x2 + (tr ? m4[12 + a] : m4[4 * a + 3]) * x3;
+                x0 = y[0]; x1 = y[1]; x2 = y[2]; x3 = y[3];
+              }
+            }
+            X[p0 * LDX + col] = x0; X[p1 * LDX + col] = x1; X[p2 * LDX + col] = x2; X[p3 * LDX + col] = x3;
+          }
+        }
+        q += run;
+      }
+      __syncwarp();
+    }
+    // Lambda = X^T Lambda_0 X into the accumulator fragments of the upper tiles
+    double c[T::NT][2];
+#pragma unroll
+    for (int t = 0; t < T::NT; ++t) c[t][0] = c[t][1] = 0.0;
+    for (int g4 = 0; g4 < d; g4 += 4) {
+      const int ra = g4 + tg, rb = g4 + (tg ^ 1);
+      const int wire = ra >> 1;
+      double sgn = 0.0;
+      int pa = 0, pb = 0;
+      if (ra < d) {
+        const bool bit = init_bits != nullptr && init_bits[wire];
+        sgn = (bit ? 1.0 : -1.0) * ((tg & 1) ? -1.0 : 1.0);
+        pa = phys[ra];
+        pb = phys[rb];
+      }
+      double af[MT], bf[MT];
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        af[t] = (ra < d) ? sgn * X[pa * LDX + 8 * t + gr] : 0.0;
+        bf[t] = (ra < d) ? X[pb * LDX + 8 * t + gr] : 0.0;
+      }
+#pragma unroll
+      for (int ti = 0; ti < MT; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < MT; ++tj) dmma_acc(c[T::idx(ti, tj)], af[ti], bf[tj]);
+    }
+    // + Lambda_y on the 2x2 diagonal blocks (both triangles of the diagonal tiles)
+    if (tg == (gr >> 1)) {
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        const int row = 8 * t + gr;
+        if (row < d) {
+          const double val = (target_bits != nullptr && target_bits[row >> 1]) ? 1.0 : -1.0;
+          if (gr & 1) c[T::idx(t, t)][0] -= val;
+          else c[T::idx(t, t)][1] += val;
+        }
+      }
+    }
+    const double pf = warp_pfaffian_tiles<MT>(c, d, scratch);
+    if (lane == 0) out[b] = ldexp(fabs(pf), -n);
+    __syncwarp();
+  }
+}
+
+int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long long B, const int8_t* init_bits,
+                       const int8_t* target_bits, double* out, cudaStream_t st) {
+  WarpCircuit wc{h->gates, h->n_gates, h->n_qubits, h->n_param_cols, h->scale, h->bias, h->consts};
+  const int d = 2 * h->n_qubits;
+  const int mt = d <= 8 ? 1 : d <= 16 ? 2 : d <= 24 ? 3 : d <= 32 ? 4 : d <= 48 ? 6 : 8;
+  const int M = 8 * mt, LDX = M + 4;
+  const int warps = 4;
+  const int gates_in_smem = h->n_gates <= 1024 ? 1 : 0;
+  const size_t gate_bytes = gates_in_smem ? (((size_t)h->n_gates * sizeof(mcb200_gate_t) + 15) & ~(size_t)15) : 0;
+  const size_t per_warp = ((((size_t)d * LDX + 128 + 6 * M) * sizeof(double) + 64) + 15) & ~(size_t)15;
+  const size_t smem = gate_bytes + warps * per_warp;
+  long long blocks = (B + warps - 1) / warps;
+  const long long cap = 32LL * kNumSMs;
+  if (blocks > cap) blocks = cap;
+  auto go = [&](auto kernel) -> int {
+    if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(expval_warp)"))
+      return rc;
+    kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(wc, params, B, init_bits, target_bits, gates_in_smem, out);
+    return check_launch("expval_warp_kernel");
+  };
+  switch (mt) {
+    case 1: return go(expval_warp_kernel<1>);
+    case 2: return go(expval_warp_kernel<2>);
+    case 3: return go(expval_warp_kernel<3>);
+    case 4: return go(expval_warp_kernel<4>);
+    case 6: return go(expval_warp_kernel<6>);
+    default: return go(expval_warp_kernel<8>);
+  }
+}
+
+}  // namespace mcb200

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/mcb200.h"
+
 namespace mcb200 {
 constexpr int kTilesMaxM = 64;
 int tiles_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out, cudaStream_t st);
@@ -14,4 +16,6 @@ long long tiles_gram_workspace_bytes(long long n0, long long n1, int d);
 int tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
                long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,
                cudaStream_t st);
+int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long long B, const int8_t* init_bits,
+                       const int8_t* target_bits, double* out, cudaStream_t st);
 }  // namespace mcb200
