@@ -343,8 +343,10 @@ extern "C" int mcb200_circuit_expval_projector(const mcb200_circuit_t* circuit_h
   if (out == nullptr) return set_error("out is NULL");
   if (c.n_param_cols > 0 && params == nullptr) return set_error("params is NULL");
   const int d = 2 * c.n_qubits;
-  if (d <= kTilesMaxM)  // one warp per instance, Lambda and the Pfaffian stay in registers (expval_warp.cu)
-    return expval_warp_launch(circuit_host, params, B, init_bits, target_bits, out, as_stream(stream));
+  if (d <= kTilesMaxM) {  // one warp per instance, Lambda and the Pfaffian stay in registers (expval_warp.cu)
+    const int rc = expval_warp_launch(circuit_host, params, B, init_bits, target_bits, out, as_stream(stream));
+    if (rc >= 0) return rc;  // -1: gate program too large for shared memory -> block-per-instance kernel below
+  }
   const size_t coef_bytes = (size_t)(c.n_qubits > 4 ? c.n_qubits : 4) * 16 * sizeof(double);
   const size_t smem = ((size_t)d * d + (size_t)d * (d + 1)) * sizeof(double) + coef_bytes;
   if (smem > (size_t)kMaxDynSmem)

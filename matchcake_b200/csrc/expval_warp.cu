@@ -61,8 +61,16 @@ __device__ __forceinline__ void wc_rotation_coef(const WarpCircuit& c, const mcb
   out[3] = s;
 }
 
+// Compact per-gate code built once per block: kind | wire0 << 3 | wire1 << 11 | transpose << 19 | run << 20, where
+// `run` counts the consecutive non-fSWAP gates (walking DOWN the list, i.e. in the order they are applied here)
+// that act on the same wire pair, this gate included.
+__device__ __forceinline__ int wc_kind(int code) { return code & 7; }
+__device__ __forceinline__ int wc_wire0(int code) { return (code >> 3) & 0xff; }
+__device__ __forceinline__ int wc_wire1(int code) { return (code >> 11) & 0xff; }
+__device__ __forceinline__ int wc_run(int code) { return (code >> 20) & 0xfff; }
+
 template <int MT>
-__global__ void __launch_bounds__(128) expval_warp_kernel(WarpCircuit wc, const double* __restrict__ params,
+__global__ void __launch_bounds__(192) expval_warp_kernel(WarpCircuit wc, const double* __restrict__ params,
                                                           long long B, const int8_t* init_bits,
                                                           const int8_t* target_bits, int gates_in_smem,
                                                           double* __restrict__ out) {
@@ -73,96 +81,116 @@ __global__ void __launch_bounds__(128) expval_warp_kernel(WarpCircuit wc, const 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = wc.n_qubits, d = 2 * n;
   const int warps = blockDim.x >> 5, w = warp_id(), lane = lane_id(), gr = lane >> 2, tg = lane & 3;
-  // shared layout: [gates (block)] [per warp: X (64 x LDX... d rows) | coef 32x4 | scratch | phys]
-  mcb200_gate_t* sg = reinterpret_cast<mcb200_gate_t*>(smem_raw);
-  const size_t gate_bytes = gates_in_smem ? (((size_t)wc.n_gates * sizeof(mcb200_gate_t) + 15) & ~(size_t)15) : 0;
+  // shared layout: [code | off (block)] [per warp: X (d x LDX) | coef 32x4 | scratch | phys]
+  int* scode = reinterpret_cast<int*>(smem_raw);
+  int* soff = scode + wc.n_gates;
+  const size_t gate_bytes = (((size_t)wc.n_gates * 2 * sizeof(int)) + 15) & ~(size_t)15;
   const size_t per_warp = ((((size_t)d * LDX + 128 + T::kScratch) * sizeof(double) + 64) + 15) & ~(size_t)15;
   unsigned char* wbase = smem_raw + gate_bytes + (size_t)w * per_warp;
   double* X = reinterpret_cast<double*>(wbase);
   double* coef = X + (size_t)d * LDX;
   double* scratch = coef + 128;
   unsigned char* phys = reinterpret_cast<unsigned char*>(scratch + T::kScratch);
-  if (gates_in_smem) {
-    for (int i = threadIdx.x; i < wc.n_gates * 6; i += blockDim.x)
-      reinterpret_cast<int32_t*>(sg)[i] = reinterpret_cast<const int32_t*>(wc.gates)[i];
-    __syncthreads();
+  for (int i = threadIdx.x; i < wc.n_gates; i += blockDim.x) {
+    const mcb200_gate_t g = wc.gates[i];
+    int run = 0;
+    if (g.kind != MCB200_GATE_FSWAP) {
+      run = 1;
+      for (int j = i - 1; j >= 0 && run < 4000; --j) {
+        const mcb200_gate_t g2 = wc.gates[j];
+        if (g2.kind == MCB200_GATE_FSWAP || g2.wire0 != g.wire0) break;
+        ++run;
+      }
+    }
+    scode[i] = g.kind | (g.wire0 << 3) | (g.wire1 << 11) | ((g.flags & MCB200_GATE_FLAG_TRANSPOSE) << 19) | (run << 20);
+    soff[i] = g.off;
   }
-  const mcb200_gate_t* gl = gates_in_smem ? sg : wc.gates;
+  __syncthreads();
 
   for (long long b = (long long)blockIdx.x * warps + w; b < B; b += (long long)gridDim.x * warps) {
     const double* prow = params + b * wc.n_param_cols;
     // X = I (lane owns column(s) lane, lane+32), phys = identity
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      const int col = lane + 32 * h;
-      if (col < M)
-        for (int r = 0; r < d; ++r) X[r * LDX + col] = (r == col) ? 1.0 : 0.0;
+    for (int e = lane; e < (d * LDX) / 2; e += 32) reinterpret_cast<double2*>(X)[e] = make_double2(0.0, 0.0);
+    __syncwarp();
+    for (int r = lane; r < d; r += 32) {
+      X[r * LDX + r] = 1.0;
+      phys[r] = (unsigned char)r;
     }
-    for (int r = lane; r < d; r += 32) phys[r] = (unsigned char)r;
     __syncwarp();
     // gates in reverse application order, 32 at a time
     for (int top = wc.n_gates - 1; top >= 0; top -= 32) {
       {
         const int gi = top - lane;
         if (gi >= 0) {
-          const mcb200_gate_t g = gl[gi];
-          if (g.kind <= MCB200_GATE_RZRZ) wc_rotation_coef(wc, g, prow, coef + 4 * lane);
+          const int code = scode[gi];
+          if (wc_kind(code) <= MCB200_GATE_RZRZ) {
+            mcb200_gate_t g;
+            g.kind = wc_kind(code);
+            g.off = soff[gi];
+            wc_rotation_coef(wc, g, prow, coef + 4 * lane);
+          }
         }
       }
       __syncwarp();
       const int cnt = top + 1 < 32 ? top + 1 : 32;
       int q = 0;
       while (q < cnt) {
-        const mcb200_gate_t g = gl[top - q];
-        if (g.kind == MCB200_GATE_FSWAP) {
-          // rows of the block: s = 2 (w1 - w0 + 1); new[0:2] = old[s-2:s], new[i] = old[i-2]  (transpose: inverse)
-          const int r0 = 2 * g.wire0, s = 2 * (g.wire1 - g.wire0 + 1);
-          // cyclic shift of the logical->physical table over [r0, r0+s)
+        const int code = scode[top - q];
+        const int r0 = 2 * wc_wire0(code);
+        if (wc_kind(code) == MCB200_GATE_FSWAP) {
+          // no data moves: cyclic shift of the logical->physical row table over [r0, r0 + s)
+          //   forward block: new[0:2] = old[s-2:s], new[i] = old[i-2];   transposed block: new[i] = old[i+2 mod s]
+          const int s = 2 * (wc_wire1(code) - wc_wire0(code) + 1);
+          const bool fwd = !((code >> 19) & 1);
           unsigned char v0 = 0, v1 = 0;
-          const bool fwd = !(g.flags & MCB200_GATE_FLAG_TRANSPOSE);
           const int i0 = lane, i1 = lane + 32;
-          if (i0 < s) v0 = phys[r0 + (fwd ? (i0 + s - 2) % s : (i0 + 2) % s)];
-          if (i1 < s) v1 = phys[r0 + (fwd ? (i1 + s - 2) % s : (i1 + 2) % s)];
+          if (i0 < s) {
+            int src = fwd ? i0 - 2 : i0 + 2;
+            src += (src < 0) ? s : ((src >= s) ? -s : 0);
+            v0 = phys[r0 + src];
+          }
+          if (H > 1 && i1 < s) {
+            int src = fwd ? i1 - 2 : i1 + 2;
+            src += (src >= s) ? -s : 0;
+            v1 = phys[r0 + src];
+          }
           __syncwarp();
           if (i0 < s) phys[r0 + i0] = v0;
-          if (i1 < s) phys[r0 + i1] = v1;
+          if (H > 1 && i1 < s) phys[r0 + i1] = v1;
           __syncwarp();
           ++q;
           continue;
         }
-        const int r0 = 2 * g.wire0;
         const int p0 = phys[r0], p1 = phys[r0 + 1], p2 = phys[r0 + 2], p3 = phys[r0 + 3];
-        // how many consecutive gates (going down the list) act on the same wire pair and are not fSWAPs
-        int run = 1;
-        while (q + run < cnt) {
-          const mcb200_gate_t g2 = gl[top - q - run];
-          if (g2.kind == MCB200_GATE_FSWAP || g2.wire0 != g.wire0) break;
-          ++run;
-        }
+        int run = wc_run(code);
+        if (run > cnt - q) run = cnt - q;  // the rest of the run continues in the next chunk of 32
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           const int col = lane + 32 * h;
           if (col < M) {
             double x0 = X[p0 * LDX + col], x1 = X[p1 * LDX + col], x2 = X[p2 * LDX + col], x3 = X[p3 * LDX + col];
             for (int u = 0; u < run; ++u) {
-              const mcb200_gate_t gu = gl[top - q - u];
-              if (gu.kind <= MCB200_GATE_RZRZ) {
-                const double4 cf = *reinterpret_cast<const double4*>(coef + 4 * (q + u));
+              const int kind = wc_kind(scode[top - q - u]);
+              if (kind <= MCB200_GATE_RZRZ) {
+                const double2 ca = *reinterpret_cast<const double2*>(coef + 4 * (q + u));
+                const double2 cb = *reinterpret_cast<const double2*>(coef + 4 * (q + u) + 2);
                 double y0, y1, y2, y3;
-                if (gu.kind == MCB200_GATE_RXRX) {        // pairs (0,3), (1,2)
-                  y0 = cf.x * x0 + cf.y * x3;  y3 = cf.x * x3 - cf.y * x0;
-                  y1 = cf.z * x1 + cf.w * x2;  y2 = cf.z * x2 - cf.w * x1;
-                } else if (gu.kind == MCB200_GATE_RYRY) { // pairs (0,2), (1,3)
-                  y0 = cf.x * x0 + cf.y * x2;  y2 = cf.x * x2 - cf.y * x0;
-                  y1 = cf.z * x1 + cf.w * x3;  y3 = cf.z * x3 - cf.w * x1;
-                } else {                                   // pairs (0,1), (2,3)
-                  y0 = cf.x * x0 + cf.y * x1;  y1 = cf.x * x1 - cf.y * x0;
-                  y2 = cf.z * x2 + cf.w * x3;  y3 = cf.z * x3 - cf.w * x2;
+                if (kind == MCB200_GATE_RXRX) {        // pairs (0,3), (1,2)
+                  y0 = ca.x * x0 + ca.y * x3;  y3 = ca.x * x3 - ca.y * x0;
+                  y1 = cb.x * x1 + cb.y * x2;  y2 = cb.x * x2 - cb.y * x1;
+                } else if (kind == MCB200_GATE_RYRY) { // pairs (0,2), (1,3)
+                  y0 = ca.x * x0 + ca.y * x2;  y2 = ca.x * x2 - ca.y * x0;
+                  y1 = cb.x * x1 + cb.y * x3;  y3 = cb.x * x3 - cb.y * x1;
+                } else {                                // pairs (0,1), (2,3)
+                  y0 = ca.x * x0 + ca.y * x1;  y1 = ca.x * x1 - ca.y * x0;
+                  y2 = cb.x * x2 + cb.y * x3;  y3 = cb.x * x3 - cb.y * x2;
                 }
                 x0 = y0; x1 = y1; x2 = y2; x3 = y3;
               } else {  // explicit 4x4 block
-                const double* m4 = (gu.kind == MCB200_GATE_BLOCK4_CONST) ? wc.consts + gu.off : prow + gu.off;
-                const bool tr = gu.flags & MCB200_GATE_FLAG_TRANSPOSE;
+                const int gcode = scode[top - q - u];
+                const int goff = soff[top - q - u];
+                const double* m4 = (kind == MCB200_GATE_BLOCK4_CONST) ? wc.consts + goff : prow + goff;
+                const bool tr = (gcode >> 19) & 1;
                 double y[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
@@ -228,11 +256,12 @@ int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long lon
   const int d = 2 * h->n_qubits;
   const int mt = d <= 8 ? 1 : d <= 16 ? 2 : d <= 24 ? 3 : d <= 32 ? 4 : d <= 48 ? 6 : 8;
   const int M = 8 * mt, LDX = M + 4;
-  const int warps = 4;
-  const int gates_in_smem = h->n_gates <= 1024 ? 1 : 0;
-  const size_t gate_bytes = gates_in_smem ? (((size_t)h->n_gates * sizeof(mcb200_gate_t) + 15) & ~(size_t)15) : 0;
+  const int warps = 6;
+  const int gates_in_smem = 1;
+  const size_t gate_bytes = (((size_t)h->n_gates * 2 * sizeof(int)) + 15) & ~(size_t)15;
   const size_t per_warp = ((((size_t)d * LDX + 128 + 6 * M) * sizeof(double) + 64) + 15) & ~(size_t)15;
   const size_t smem = gate_bytes + warps * per_warp;
+  if (smem > (size_t)kMaxDynSmem) return -1;  // caller falls back to the block-per-instance kernel
   long long blocks = (B + warps - 1) / warps;
   const long long cap = 32LL * kNumSMs;
   if (blocks > cap) blocks = cap;
