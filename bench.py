@@ -209,9 +209,7 @@ def main():
         n, B = 16, 65536
         circ = mops.CompiledCircuit(n, readme_gate_specs(n, mops), 2, device=dev)
         pool_n = max(8, (2 * L2_BYTES) // (B * 2 * 8) + 1)  # rotating inputs: pool > 2 x L2
-        pool = [torch.as_tensor(rng.uniform(0, 2 * np.pi, (B, 2))).to(dev) for _ in range(min(pool_n, K + W + 1))]
-        while len(pool) < pool_n and len(pool) < 8:
-            pool.append(pool[0].clone())
+        pool = [torch.as_tensor(rng.uniform(0, 2 * np.pi, (B, 2))).to(dev) for _ in range(pool_n)]
         gathered = torch.empty((ws * B,), dtype=torch.float64, device=dev) if ws > 1 else None
 
         def step(i):
@@ -225,7 +223,7 @@ def main():
         cfg = {"workload": "c2: N=16 README CompRxRx/RyRy/RzRz+fSWAP circuit, projector |0..0>, batch 65536 per GPU",
                "n_qubits": n, "batch_per_gpu": B, "parallelism": f"batch sharded x{ws}, one all-gather of the outputs",
                "l2": f"rotating pool of {len(pool)} input buffers ({len(pool) * B * 16 / 2**20:.0f} MiB > 126 MiB L2)"}
-        kernel_name = "circuit_expval_projector_kernel"
+        kernel_name = "expval_warp_kernel<4>"
         alg_flops_per_launch = c2_flops_per_unit(n) * B
         launches_per_step = 1
         # end-to-end through the device API with pinned host params and a host read of the result
@@ -274,7 +272,7 @@ def main():
         cfg = {"workload": "c3: N=32 FermionicPQCKernel(rotations='X,Z') Gram 8192x8192, 33550336 evaluated cells",
                "n_qubits": n, "n_samples": ns, "parallelism": f"Gram rows sharded x{ws}, one all-gather",
                "l2": "per-sample covariances 268 MB > 126 MiB L2"}
-        kernel_name = "gram_warp_kernel"
+        kernel_name = "gram_tiles_kernel<8,2,4>"
         alg_flops_per_launch = gram_flops_per_entry(2 * n) * entries / ws
         launches_per_step = None
         h2d, d2h = ns * 2 * n * 8, ns * ns * 8
@@ -295,7 +293,7 @@ def main():
         def step(i):
             xcols = mops.circuit_columns(circ, params, maj)
             cov = mops.cov_basis(xcols, n)
-            return mops.probs(cov, states, normalize=True)
+            return mops.probs_all(cov, normalize=True)
 
         e2e_step = None
         units_per_step = B * ws

@@ -125,6 +125,13 @@ int mcb200_pfaffian(const double* A, int64_t n, int32_t m, int32_t mode, double 
 int mcb200_probs(const double* cov, const int8_t* outcomes, int64_t B, int32_t Q, int32_t k,
                  int32_t normalize, double* out, void* stream);
 
+/* All 2^k outcomes of k measured wires at once (qml.probs, nif_device.py:430-479): out[b, q], outcome index q
+ * MSB first (states_to_binary, nif_device.py:151-165).  The 2^k Pfaffians share a binary tree of partial
+ * eliminations (k <= 10); wider marginals enumerate the outcomes into `workspace` and call mcb200_probs. */
+int64_t mcb200_probs_all_workspace_bytes(int32_t k);
+int mcb200_probs_all(const double* cov, int64_t B, int32_t k, int32_t normalize, double* out,
+                     void* workspace, void* stream);
+
 /* Pauli-sum read-out, two steps so that the summation order is deterministic:
  *   feats[b, t] = Pf(cov[b][S_t, S_t])  for index_sets (T, s) int32 (sorted Majorana index sets of ONE parity
  *   sector of size s; s = 0 -> 1, s = 2 -> direct gather), cov (B, D, D);

@@ -47,6 +47,8 @@ SIGNATURES = {
     "mcb200_pfaffian_workspace_bytes": (c_i64, [c_i64, c_i32]),
     "mcb200_pfaffian": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_f64, c_vp, c_vp, c_vp]),
     "mcb200_probs": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "mcb200_probs_all_workspace_bytes": (c_i64, [c_i32]),
+    "mcb200_probs_all": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "mcb200_sector_features": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "mcb200_rowdot": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "mcb200_circuit_expval_projector": (c_i32, [C.POINTER(CircuitStruct), c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),

@@ -142,6 +142,15 @@ __global__ void rowdot_kernel(const double* feats, const double* coeffs, long lo
   if (lane_id() == 0) out[row] = accumulate ? out[row] + s : s;
 }
 
+__global__ void enumerate_outcomes_kernel(int8_t* bits, int k) {
+  // states_to_binary (nif_device.py:151-165): outcome index -> bits, MSB first
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ((long long)k << k)) return;
+  long long q = e / k;
+  int j = (int)(e - q * k);
+  bits[e] = (int8_t)((q >> (k - 1 - j)) & 1);
+}
+
 constexpr int kWarpKernelMaxM = 128;
 constexpr int kBlockGlobalCtas = 4 * kNumSMs;
 
@@ -407,3 +416,21 @@ extern "C" int mcb200_gram_symmetrize(double* K, int64_t n0, int64_t n1, int64_t
   gram_symmetrize_kernel<<<(unsigned)((q * q + 255) / 256), 256, 0, as_stream(stream)>>>(K, n0, n1, ldk);
   return check_launch("gram_symmetrize_kernel");
 }
+
+extern "C" int mcb200_probs_all(const double* cov, int64_t B, int32_t k, int32_t normalize, double* out,
+                                void* workspace, void* stream) {
+  if (B < 0 || k < 1 || k > 20) return set_error("probs_all: bad sizes (k=%d)", k);
+  if (B == 0) return 0;
+  if (cov == nullptr || out == nullptr) return set_error("probs_all: NULL pointer");
+  cudaStream_t st = as_stream(stream);
+  const int rc = tiles_probs_all(cov, B, k, normalize, out, st);
+  if (rc >= 0) return rc;
+  // wide marginals: enumerate the outcomes (workspace holds the 2^k x k bit table) and use the per-outcome path
+  if (workspace == nullptr) return set_error("probs_all: k=%d needs a workspace (mcb200_probs_all_workspace_bytes)", k);
+  const long long Q = 1LL << k;
+  enumerate_outcomes_kernel<<<(unsigned)((Q * k + 255) / 256), 256, 0, st>>>((int8_t*)workspace, k);
+  if (int rc2 = check_launch("enumerate_outcomes_kernel")) return rc2;
+  return mcb200_probs(cov, (const int8_t*)workspace, B, (int32_t)Q, k, normalize, out, stream);
+}
+
+extern "C" int64_t mcb200_probs_all_workspace_bytes(int32_t k) { return k <= 10 ? 0 : ((int64_t)k << k); }

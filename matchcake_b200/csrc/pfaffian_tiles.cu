@@ -248,3 +248,116 @@ int tiles_gram(const double* cov0, const double* cov1, long long n0, long long n
 }
 
 }  // namespace mcb200
+
+// ------------------------------------------------------------------------------------------- probs over ALL outcomes
+// qml.probs(wires) asks for p(y) = 2^-k |Pf(Lambda|_W + Lambda_y)| for every y in {0,1}^k (nif_device.py:430-479).
+// Eliminating the wire pairs in order WITHOUT pivoting, the pivot of wire j is
+//     piv_j = A^(j)[0][1] -+ 1 = 2 p(y_j | y_0..y_{j-1}),
+// and it only depends on the outcome prefix, so the 2^k Pfaffians share a binary tree of partial eliminations:
+// 2^(j+1) rank-2 updates of size (2k-2j-2)^2 at level j instead of 2^k full Pfaffians (70x less work at k = 8).
+// A vanishing pivot means the whole subtree has probability 0, so no pivoting is needed: sub-trees whose
+// conditional probability is below 1e-14 are set to exactly 0 (absolute error <= 5e-15 on outcomes that the
+// reference returns as ~1e-16 noise).  One warp per circuit instance, nodes ping-pong through shared memory.
+namespace mcb200 {
+
+__global__ void __launch_bounds__(128) probs_tree_kernel(const double* __restrict__ cov, long long B, int k,
+                                                         int normalize, int buf_doubles, double* __restrict__ out) {
+  extern __shared__ double smem[];
+  const int m = 2 * k, Q = 1 << k;
+  const int lane = lane_id(), warps = blockDim.x >> 5;
+  double* base = smem + (size_t)warp_id() * (2 * (size_t)buf_doubles + 2 * (size_t)Q);
+  double* bufA = base;
+  double* bufB = base + buf_doubles;
+  double* fA = base + 2 * (size_t)buf_doubles;
+  double* fB = fA + Q;
+  for (long long b = (long long)blockIdx.x * warps + warp_id(); b < B; b += (long long)gridDim.x * warps) {
+    const double* a = cov + b * (long long)m * m;
+    for (int e = lane; e < m * m; e += 32) bufA[e] = a[e];
+    if (lane == 0) fA[0] = 1.0;
+    __syncwarp();
+    double* cur = bufA; double* nxt = bufB; double* fc = fA; double* fn = fB;
+    for (int j = 0; j < k; ++j) {
+      const int s = m - 2 * j, s2 = s - 2, nodes = 1 << j;
+      const int ss = s * s, ss2 = s2 * s2;
+      // children c = 2 * node + y
+      for (int c = lane; c < 2 * nodes; c += 32) {
+        const double* T = cur + (size_t)(c >> 1) * ss;
+        const double piv = T[1] + ((c & 1) ? 1.0 : -1.0);
+        const double f = fc[c >> 1];
+        fn[c] = (fabs(piv) < 1e-14 || f == 0.0) ? 0.0 : f * piv;
+      }
+      __syncwarp();
+      if (s2 > 0) {
+        if (ss2 >= 64) {  // lanes over the elements of one child
+          for (int c = 0; c < 2 * nodes; ++c) {
+            const double* T = cur + (size_t)(c >> 1) * ss;
+            double* U = nxt + (size_t)c * ss2;
+            const double piv = T[1] + ((c & 1) ? 1.0 : -1.0);
+            const bool dead = fn[c] == 0.0;
+            const double inv = dead ? 0.0 : 1.0 / piv;
+            for (int e = lane; e < ss2; e += 32) {
+              const int ra = e / s2, rb = e - ra * s2;
+              if (rb > ra) {
+                const double ta = T[ra + 2] * inv, tb = T[rb + 2] * inv;          // tau = T[0][.] / piv
+                U[e] = T[(ra + 2) * s + rb + 2] - ta * T[s + rb + 2] + T[s + ra + 2] * tb;
+              }
+            }
+          }
+        } else {          // lanes over the children
+          for (int c = lane; c < 2 * nodes; c += 32) {
+            const double* T = cur + (size_t)(c >> 1) * ss;
+            double* U = nxt + (size_t)c * ss2;
+            const double piv = T[1] + ((c & 1) ? 1.0 : -1.0);
+            const bool dead = fn[c] == 0.0;
+            const double inv = dead ? 0.0 : 1.0 / piv;
+            for (int ra = 0; ra < s2 - 1; ++ra) {
+              const double ta = T[ra + 2] * inv, wa = T[s + ra + 2];
+              for (int rb = ra + 1; rb < s2; ++rb)
+                U[ra * s2 + rb] = T[(ra + 2) * s + rb + 2] - ta * T[s + rb + 2] + wa * (T[rb + 2] * inv);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      double* t = cur; cur = nxt; nxt = t;
+      t = fc; fc = fn; fn = t;
+    }
+    // leaves: fc[q] = prod of pivots = Pf; p = 2^-k |Pf|
+    double sum = 0.0;
+    for (int q = lane; q < Q; q += 32) {
+      const double p = ldexp(fabs(fc[q]), -k);
+      fc[q] = p;
+      sum += p;
+    }
+    if (normalize) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    double* o = out + b * (long long)Q;
+    for (int q = lane; q < Q; q += 32) o[q] = normalize ? fc[q] / sum : fc[q];
+    __syncwarp();
+  }
+}
+
+int tiles_probs_all(const double* cov, long long B, int k, int normalize, double* out, cudaStream_t st) {
+  const int m = 2 * k;
+  size_t buf = (size_t)m * m;
+  for (int j = 0; j <= k; ++j) {
+    const size_t w = ((size_t)1 << j) * (size_t)(m - 2 * j) * (m - 2 * j);
+    if (w > buf) buf = w;
+  }
+  const size_t per_warp = (2 * buf + 2 * ((size_t)1 << k)) * sizeof(double);
+  int warps = 4;
+  while (warps > 1 && warps * per_warp > 96 * 1024) warps >>= 1;
+  const size_t smem = warps * per_warp;
+  if (smem > (size_t)kMaxDynSmem) return -1;
+  if (int rc = check_cuda(cudaFuncSetAttribute(probs_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(probs_tree)"))
+    return rc;
+  long long blocks = (B + warps - 1) / warps;
+  if (blocks > 16LL * kNumSMs) blocks = 16LL * kNumSMs;
+  probs_tree_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(cov, B, k, normalize, (int)buf, out);
+  return check_launch("probs_tree_kernel");
+}
+
+}  // namespace mcb200

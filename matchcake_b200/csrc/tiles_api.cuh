@@ -16,6 +16,8 @@ long long tiles_gram_workspace_bytes(long long n0, long long n1, int d);
 int tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
                long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,
                cudaStream_t st);
+// every outcome of k measured wires at once (outcome index MSB first); returns -1 if k is too large for the tree kernel
+int tiles_probs_all(const double* cov, long long B, int k, int normalize, double* out, cudaStream_t st);
 int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long long B, const int8_t* init_bits,
                        const int8_t* target_bits, double* out, cudaStream_t st);
 }  // namespace mcb200

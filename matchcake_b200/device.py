@@ -526,8 +526,7 @@ class NonInteractingFermionicDevice:
         maj = np.stack([2 * widx, 2 * widx + 1], axis=1).ravel()
         self._compile()
         cov = self._cov_device(maj)
-        outcomes = torch.as_tensor(np.ascontiguousarray(states.astype(np.int8)), device=self.torch_device)
-        p = _ops.probs(cov, outcomes, normalize=True)
+        p = _ops.probs_all(cov, normalize=True)
         batched = self._batched or self._state_prep_op.batch_size is not None
         return self._out(p if batched else p[0])
 

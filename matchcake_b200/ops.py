@@ -240,6 +240,20 @@ def probs(cov: torch.Tensor, outcomes: torch.Tensor, normalize: bool = False) ->
     return out
 
 
+def probs_all(cov: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+    """Every outcome of the k measured wires: out[b, q] for q in range(2^k), MSB first; cov (B, 2k, 2k)."""
+    cov = _f64(cov, "cov")
+    B, m, _ = cov.shape
+    k = m // 2
+    if m != 2 * k or k < 1:
+        raise ValueError("cov must be (B, 2k, 2k)")
+    out = torch.empty((B, 1 << k), dtype=torch.float64, device=cov.device)
+    lib = _lib.load()
+    ws = _workspace(lib.mcb200_probs_all_workspace_bytes(k), cov.device)
+    check(lib.mcb200_probs_all(_ptr(cov), B, k, int(normalize), _ptr(out), _ptr(ws), _stream()))
+    return out
+
+
 def sector_features(cov: torch.Tensor, index_sets: torch.Tensor) -> torch.Tensor:
     """feats[b, t] = Pf(cov[b][S_t, S_t]); cov (B, D, D), index_sets (T, s)."""
     cov = _f64(cov, "cov")

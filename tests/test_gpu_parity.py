@@ -173,6 +173,49 @@ def test_cov_basis_and_probs(n, k):
                                    rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("n,k,product", [(4, 4, False), (6, 3, True), (10, 8, False), (12, 10, True), (12, 11, False), (5, 1, True)])
+def test_probs_all_tree(n, k, product):
+    """All 2^k outcomes at once (shared elimination tree) == the reference's per-outcome formula, normalised or not."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(100 * n + k)
+    B = 5
+    r = gates.random_sptm(n, seed=n + k, batch_size=B)
+    if product:
+        amp = rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))
+        amp /= np.linalg.norm(amp, axis=1, keepdims=True)
+    else:
+        amp = cv.amplitudes_from_basis_state(rng.integers(0, 2, n))
+    wires = rng.permutation(n)[:k]
+    maj = readout.majorana_indices_of_wires(wires)
+    cov_ref = cv.evolve(cv.covariance_matrix(amp), r)[:, maj[:, None], maj[None, :]]
+    states = readout.states_to_binary(np.arange(2 ** k), k)
+    ref = np.stack([readout.probs_product_state(cv.evolve(cv.covariance_matrix(amp), r)[b], states, wires) for b in range(B)])
+    out = mops.probs_all(dev(cov_ref)).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+    outn = mops.probs_all(dev(cov_ref), normalize=True).cpu().numpy()
+    np.testing.assert_allclose(outn, ref / ref.sum(axis=1, keepdims=True), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(out, mops.probs(dev(cov_ref), torch.as_tensor(states.copy())).cpu().numpy(),
+                               rtol=RTOL, atol=ATOL)
+
+
+def test_probs_all_parity_forbidden_outcomes_are_exact_zeros():
+    """Basis-state input measured on ALL wires: half of the outcomes violate fermion parity -> exactly 0."""
+    from matchcake_b200 import ops as mops
+
+    n = 6
+    rng = np.random.default_rng(7)
+    ops = readme_ops(n, rng.uniform(0, 6, (3, 2)), matchgate=False)
+    r = gates.chain(ops, n, contraction=None)
+    bits = np.array([1, 0, 0, 1, 0, 0])
+    cov_ref = cv.evolve(cv.covariance_matrix(cv.amplitudes_from_basis_state(bits)), r)
+    out = mops.probs_all(dev(cov_ref), normalize=True).cpu().numpy()
+    ref = readout.analytic_probability(r, cv.amplitudes_from_basis_state(bits), np.arange(n))
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+    odd = np.array([bin(q).count("1") % 2 for q in range(2 ** n)]) != bits.sum() % 2
+    assert np.all(out[:, odd] == 0.0)
+
+
 def test_fused_expval_projector_golden_and_batch():
     from matchcake_b200 import ops as mops
 
