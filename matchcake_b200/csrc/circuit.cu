@@ -21,8 +21,8 @@ struct CircuitDev {
   const double* consts;
 };
 
-// Coefficients of one gate for one circuit instance: 16 doubles (row-major 4x4) for BLOCK4 kinds,
-// {c1, t1, c2, t2} for the three rotation kinds (two independent Givens pairs), nothing for FSWAP.
+// Coefficients of one rotation gate for one circuit instance: {c1, t1, c2, t2} (two independent Givens pairs).
+// Explicit 4x4 blocks are read from consts / the parameter row when they are applied; fSWAPs need none.
 __device__ __forceinline__ double load_angle(const CircuitDev& c, const double* prow, int col) {
   double x = prow[col];
   if (c.scale != nullptr) x = c.bias[col] + c.scale[col] * x;
@@ -64,109 +64,135 @@ __device__ void gate_coefficients(const CircuitDev& c, const mcb200_gate_t& g, c
       out[3] = s;
       break;
     }
-    case MCB200_GATE_BLOCK4_CONST: {
-      for (int i = 0; i < 16; ++i) {
-        int src = (g.flags & MCB200_GATE_FLAG_TRANSPOSE) ? (i % 4) * 4 + i / 4 : i;
-        out[i] = c.consts[g.off + src];
-      }
-      break;
-    }
-    case MCB200_GATE_BLOCK4_PARAM: {
-      for (int i = 0; i < 16; ++i) {
-        int src = (g.flags & MCB200_GATE_FLAG_TRANSPOSE) ? (i % 4) * 4 + i / 4 : i;
-        out[i] = prow[g.off + src];
-      }
-      break;
-    }
     default:
       break;
   }
 }
 
-// x <- G x on rows r0..r0+3 of column `col` of X.
-__device__ __forceinline__ void apply_gate_column(const mcb200_gate_t& g, const double* cf, double* X, int ld,
-                                                  int col, int d) {
-  double* x = X + (2 * g.wire0) * ld + col;
+// x <- G x on rows 2*wire0 .. of the columns cc = first, first + step, ... < mc of X (one gate, many columns).
+__device__ __forceinline__ void apply_gate_columns(const CircuitDev& c, const mcb200_gate_t& g, const double* cf,
+                                                   const double* prow, double* X, int ld, int first, int step,
+                                                   int mc) {
+  double* xb = X + (2 * g.wire0) * ld;
   switch (g.kind) {
-    case MCB200_GATE_RXRX: {
-      double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
-      x[0] = cf[0] * x0 + cf[1] * x3;
-      x[3 * ld] = cf[0] * x3 - cf[1] * x0;
-      x[ld] = cf[2] * x1 + cf[3] * x2;
-      x[2 * ld] = cf[2] * x2 - cf[3] * x1;
+    case MCB200_GATE_RXRX: {  // Givens pairs (0,3), (1,2)
+      const double c1 = cf[0], t1 = cf[1], c2 = cf[2], t2 = cf[3];
+      for (int cc = first; cc < mc; cc += step) {
+        double* x = xb + cc;
+        const double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
+        x[0] = c1 * x0 + t1 * x3;
+        x[3 * ld] = c1 * x3 - t1 * x0;
+        x[ld] = c2 * x1 + t2 * x2;
+        x[2 * ld] = c2 * x2 - t2 * x1;
+      }
       break;
     }
-    case MCB200_GATE_RYRY: {
-      double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
-      x[0] = cf[0] * x0 + cf[1] * x2;
-      x[2 * ld] = cf[0] * x2 - cf[1] * x0;
-      x[ld] = cf[2] * x1 + cf[3] * x3;
-      x[3 * ld] = cf[2] * x3 - cf[3] * x1;
+    case MCB200_GATE_RYRY: {  // pairs (0,2), (1,3)
+      const double c1 = cf[0], t1 = cf[1], c2 = cf[2], t2 = cf[3];
+      for (int cc = first; cc < mc; cc += step) {
+        double* x = xb + cc;
+        const double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
+        x[0] = c1 * x0 + t1 * x2;
+        x[2 * ld] = c1 * x2 - t1 * x0;
+        x[ld] = c2 * x1 + t2 * x3;
+        x[3 * ld] = c2 * x3 - t2 * x1;
+      }
       break;
     }
-    case MCB200_GATE_RZRZ: {
-      double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
-      x[0] = cf[0] * x0 + cf[1] * x1;
-      x[ld] = cf[0] * x1 - cf[1] * x0;
-      x[2 * ld] = cf[2] * x2 + cf[3] * x3;
-      x[3 * ld] = cf[2] * x3 - cf[3] * x2;
+    case MCB200_GATE_RZRZ: {  // pairs (0,1), (2,3)
+      const double c1 = cf[0], t1 = cf[1], c2 = cf[2], t2 = cf[3];
+      for (int cc = first; cc < mc; cc += step) {
+        double* x = xb + cc;
+        const double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
+        x[0] = c1 * x0 + t1 * x1;
+        x[ld] = c1 * x1 - t1 * x0;
+        x[2 * ld] = c2 * x2 + t2 * x3;
+        x[3 * ld] = c2 * x3 - t2 * x2;
+      }
       break;
     }
     case MCB200_GATE_FSWAP: {  // sptm_fswap.py:12-27
       const int s = 2 * (g.wire1 - g.wire0 + 1);
-      if (s == 4) {
-        double x0 = x[0], x1 = x[ld];
-        x[0] = x[2 * ld];
-        x[ld] = x[3 * ld];
-        x[2 * ld] = x0;
-        x[3 * ld] = x1;
-      } else if (!(g.flags & MCB200_GATE_FLAG_TRANSPOSE)) {
-        // new[0:2] = old[s-2:s], new[i] = old[i-2]
-        double a = x[(s - 2) * ld], b = x[(s - 1) * ld];
-        for (int i = s - 1; i >= 2; --i) x[i * ld] = x[(i - 2) * ld];
-        x[0] = a;
-        x[ld] = b;
-      } else {
-        // new[i] = old[i+2], new[s-2:s] = old[0:2]
-        double a = x[0], b = x[ld];
-        for (int i = 0; i < s - 2; ++i) x[i * ld] = x[(i + 2) * ld];
-        x[(s - 2) * ld] = a;
-        x[(s - 1) * ld] = b;
+      for (int cc = first; cc < mc; cc += step) {
+        double* x = xb + cc;
+        if (s == 4) {
+          const double x0 = x[0], x1 = x[ld];
+          x[0] = x[2 * ld];
+          x[ld] = x[3 * ld];
+          x[2 * ld] = x0;
+          x[3 * ld] = x1;
+        } else if (!(g.flags & MCB200_GATE_FLAG_TRANSPOSE)) {  // new[0:2] = old[s-2:s], new[i] = old[i-2]
+          const double a = x[(s - 2) * ld], b = x[(s - 1) * ld];
+          for (int i = s - 1; i >= 2; --i) x[i * ld] = x[(i - 2) * ld];
+          x[0] = a;
+          x[ld] = b;
+        } else {                                                // new[i] = old[i+2], new[s-2:s] = old[0:2]
+          const double a = x[0], b = x[ld];
+          for (int i = 0; i < s - 2; ++i) x[i * ld] = x[(i + 2) * ld];
+          x[(s - 2) * ld] = a;
+          x[(s - 1) * ld] = b;
+        }
       }
       break;
     }
-    default: {  // BLOCK4_*
-      double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
-      x[0] = cf[0] * x0 + cf[1] * x1 + cf[2] * x2 + cf[3] * x3;
-      x[ld] = cf[4] * x0 + cf[5] * x1 + cf[6] * x2 + cf[7] * x3;
-      x[2 * ld] = cf[8] * x0 + cf[9] * x1 + cf[10] * x2 + cf[11] * x3;
-      x[3 * ld] = cf[12] * x0 + cf[13] * x1 + cf[14] * x2 + cf[15] * x3;
+    default: {  // BLOCK4_*: explicit real 4x4 block (optionally transposed)
+      const double* m4 = (g.kind == MCB200_GATE_BLOCK4_CONST) ? c.consts + g.off : prow + g.off;
+      const bool tr = g.flags & MCB200_GATE_FLAG_TRANSPOSE;
+      double mm[16];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 4; ++b2) mm[4 * a + b2] = tr ? m4[4 * b2 + a] : m4[4 * a + b2];
+      for (int cc = first; cc < mc; cc += step) {
+        double* x = xb + cc;
+        const double x0 = x[0], x1 = x[ld], x2 = x[2 * ld], x3 = x[3 * ld];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) x[a * ld] = mm[4 * a] * x0 + mm[4 * a + 1] * x1 + mm[4 * a + 2] * x2 + mm[4 * a + 3] * x3;
+      }
       break;
     }
   }
 }
 
-// Build X = R[:, cols[c0 .. c0+mc)] in shared memory (d x mc, leading dimension ld).  coef: 16 doubles per gate
-// of the widest layer.  All threads of the block participate.
+// Build X = R[:, cols[c0 .. c0+mc)] in shared memory (d x mc, leading dimension ld).  coef holds the rotation
+// coefficients (4 doubles per gate) of up to coef_cap gates: whole layers are batched so that the sincos phase keeps
+// every thread busy and costs one barrier per batch instead of one per layer.  All threads of the block participate.
 __device__ void build_columns(const CircuitDev& c, const double* prow, const int32_t* cols, int c0, int mc,
-                              double* X, int ld, double* coef) {
+                              double* X, int ld, double* coef, int coef_cap) {
   const int d = 2 * c.n_qubits;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  const int shift = ((mc & (mc - 1)) == 0) ? (31 - __clz(mc)) : -1;  // mc power of two: index split by shift
   for (int idx = tid; idx < d * mc; idx += nthr) {
-    int r = idx / mc, cc = idx - r * mc;
+    int r = shift >= 0 ? (idx >> shift) : idx / mc, cc = idx - r * mc;
     int col = cols ? cols[c0 + cc] : c0 + cc;
     X[r * ld + cc] = (r == col) ? 1.0 : 0.0;
   }
   __syncthreads();
-  for (int l = c.n_layers - 1; l >= 0; --l) {
-    const int g0 = c.layer_ptr[l], ng = c.layer_ptr[l + 1] - g0;
-    for (int g = tid; g < ng; g += nthr) gate_coefficients(c, c.gates[g0 + g], prow, coef + 16 * g);
-    __syncthreads();
-    for (int it = tid; it < ng * mc; it += nthr) {
-      int g = it / mc, cc = it - g * mc;
-      apply_gate_column(c.gates[g0 + g], coef + 16 * g, X, ld, cc, d);
+  int l = c.n_layers - 1;
+  while (l >= 0) {
+    const int ge = c.layer_ptr[l + 1];
+    int lb = l;
+    while (lb > 0 && ge - c.layer_ptr[lb - 1] <= coef_cap) --lb;
+    const int gb = c.layer_ptr[lb];
+    for (int g = gb + tid; g < ge; g += nthr) {
+      const mcb200_gate_t gt = c.gates[g];
+      if (gt.kind <= MCB200_GATE_RZRZ) gate_coefficients(c, gt, prow, coef + 4 * (g - gb));
     }
     __syncthreads();
+    // a work item = (gate, column group): the gate record and its coefficients are read once and reused for
+    // every column of the group (columns cc = group, group + CG, ...)
+    const int CG = mc >= 4 ? 4 : mc;
+    for (int ll = l; ll >= lb; --ll) {
+      const int g0 = c.layer_ptr[ll], ng = c.layer_ptr[ll + 1] - g0;
+      for (int it = tid; it < ng * CG; it += nthr) {
+        const int g = (CG == 4) ? (it >> 2) : it / CG, grp = it - g * CG;
+        const mcb200_gate_t gt = c.gates[g0 + g];
+        const double* cf = coef + 4 * (g0 + g - gb);
+        apply_gate_columns(c, gt, cf, prow, X, ld, grp, CG, mc);
+      }
+      __syncthreads();
+    }
+    l = lb - 1;
   }
 }
 
@@ -178,13 +204,14 @@ __global__ void circuit_columns_kernel(CircuitDev c, const double* __restrict__ 
   const long long b = blockIdx.x;
   const int c0 = blockIdx.y * mc;
   const int mcur = min(mc, m - c0);
+  const int ld = mc | 1;  // odd leading dimension: the 4-row blocks of different gates fall into different banks
   double* X = smem;
-  double* coef = X + (size_t)d * mc;
-  build_columns(c, params + b * c.n_param_cols, cols, c0, mcur, X, mc, coef);
+  double* coef = X + (size_t)d * ld;
+  build_columns(c, params + b * c.n_param_cols, cols, c0, mcur, X, ld, coef, max_layer_gates);
   double* out = X_out + b * (long long)d * m;
   for (int idx = threadIdx.x; idx < d * mcur; idx += blockDim.x) {
     int r = idx / mcur, cc = idx - r * mcur;
-    out[(long long)r * m + c0 + cc] = X[r * mc + cc];
+    out[(long long)r * m + c0 + cc] = X[r * ld + cc];
   }
 }
 
@@ -251,7 +278,7 @@ __global__ void circuit_expval_projector_kernel(CircuitDev c, const double* __re
   double* coef = A + (size_t)d * (d + 1);
   double* red = coef;                  // reused after the circuit phase
   const int lda = d + 1;
-  build_columns(c, params + b * c.n_param_cols, nullptr, 0, d, X, d, coef);
+  build_columns(c, params + b * c.n_param_cols, nullptr, 0, d, X, d, coef, n > 16 ? n : 16);
   cov_basis_upper(X, d, n, d, init_bits, A, lda);
   __syncthreads();
   // + Lambda_y: (Lambda_y)[2j][2j+1] = -(-1)^{y_j}   (product_state_strategy.py:89-91)
@@ -295,12 +322,13 @@ extern "C" int mcb200_circuit_columns(const mcb200_circuit_t* circuit_host, cons
   if (X_out == nullptr) return set_error("X_out is NULL");
   if (c.n_param_cols > 0 && params == nullptr) return set_error("params is NULL");
   const int d = 2 * c.n_qubits;
-  const int max_layer_gates = c.n_qubits;  // a layer holds gates on disjoint wires: at most N of them
+  // coefficient buffer: at least one full layer (<= N gates on disjoint wires), normally 256 gates per batch
+  const int max_layer_gates = c.n_qubits > 256 ? c.n_qubits : 256;
   // column chunk so that X (d x mc) + coefficients fit in shared memory
-  const size_t coef_bytes = (size_t)max_layer_gates * 16 * sizeof(double);
+  const size_t coef_bytes = (size_t)max_layer_gates * 4 * sizeof(double);
   int mc = m;
-  while ((size_t)d * mc * sizeof(double) + coef_bytes > 160 * 1024 && mc > 1) mc = (mc + 1) / 2;
-  const size_t smem = (size_t)d * mc * sizeof(double) + coef_bytes;
+  while ((size_t)d * (mc | 1) * sizeof(double) + coef_bytes > 160 * 1024 && mc > 1) mc = (mc + 1) / 2;
+  const size_t smem = (size_t)d * (mc | 1) * sizeof(double) + coef_bytes;
   if (smem > (size_t)kMaxDynSmem) return set_error("circuit_columns: d=%d does not fit shared memory", d);
   if (int rc = check_cuda(cudaFuncSetAttribute(circuit_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem), "cudaFuncSetAttribute(circuit_columns)"))
@@ -347,7 +375,7 @@ extern "C" int mcb200_circuit_expval_projector(const mcb200_circuit_t* circuit_h
     const int rc = expval_warp_launch(circuit_host, params, B, init_bits, target_bits, out, as_stream(stream));
     if (rc >= 0) return rc;  // -1: gate program too large for shared memory -> block-per-instance kernel below
   }
-  const size_t coef_bytes = (size_t)(c.n_qubits > 4 ? c.n_qubits : 4) * 16 * sizeof(double);
+  const size_t coef_bytes = (size_t)(c.n_qubits > 16 ? c.n_qubits : 16) * 4 * sizeof(double);
   const size_t smem = ((size_t)d * d + (size_t)d * (d + 1)) * sizeof(double) + coef_bytes;
   if (smem > (size_t)kMaxDynSmem)
     return set_error("circuit_expval_projector: %d qubits exceed the fused kernel's shared memory (max 59)",

@@ -27,6 +27,19 @@ elif what == "gram":
     k.fit(x)
     for _ in range(2):
         out = k(torch.as_tensor(x).to(dev))
+elif what == "c4":
+    n, B, depth, k = 64, size or 4096, 64, 8
+    gates = []; off = 0
+    kinds = (mops.GATE_RXRX, mops.GATE_RYRY, mops.GATE_RZRZ)
+    for l in range(depth):
+        for w in range(l % 2, n - 1, 2):
+            gates.append(mops.GateSpec(kinds[l % 3], w, w + 1, off)); off += 2
+    circ = mops.CompiledCircuit(n, gates, off)
+    params = torch.rand((B, off), dtype=torch.float64, device=dev) * (2 * np.pi)
+    maj = torch.arange(2 * k, dtype=torch.int32, device=dev)
+    for _ in range(2):
+        x = mops.circuit_columns(circ, params, maj)
+        out = mops.probs_all(mops.cov_basis(x, n), normalize=True)
 elif what == "pf":
     m = size or 64
     a = torch.randn(20000, m, m, dtype=torch.float64, device=dev)
