@@ -361,3 +361,4 @@ int tiles_probs_all(const double* cov, long long B, int k, int normalize, double
 }
 
 }  // namespace mcb200
+
