@@ -29,6 +29,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 L2_BYTES = 126 * 1024 * 1024
+WORKLOADS = {
+    "c2": "c2: N=16 README CompRxRx/RyRy/RzRz+fSWAP circuit, projector |0..0> expval, batch 65536 per GPU (BASELINE configs[1])",
+    "c3": "c3: N=32 FermionicPQCKernel(rotations='X,Z') Gram 8192x8192, 33550336 evaluated cells (BASELINE configs[2])",
+    "c4": "c4: N=64 depth-64 brickwork matchgate circuit, probs over 8 wires (256 outcomes), batch 16384 per GPU (BASELINE configs[3])",
+}
+# DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r01/ncu_*.txt)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")
 
 
 # ----------------------------------------------------------------------------------------------- helpers
@@ -122,8 +129,7 @@ def run_reference(args):
         params = rng.uniform(0, 2 * np.pi, (bs, 2))
         step = lambda: ref_torch.readme_expvals(params, n)
         units, metric, unit = bs, "circuit_expvals_per_sec", "expvals/s"
-        cfg = {"workload": "c2: N=16 README CompRxRx/RyRy/RzRz+fSWAP circuit, projector |0..0>, fp64",
-               "batch_per_step": bs}
+        cfg = {"workload": WORKLOADS["c2"], "n_qubits": n, "batch_per_step": bs}
         sample = f"{bs} circuit instances per step (full config: 65536)"
     elif args.workload == "c3":
         n, ns = 32, 96
@@ -133,7 +139,7 @@ def run_reference(args):
         idx = np.stack(np.tril_indices(ns, -1), axis=1)
         step = lambda: ref_torch.gram_pairs(s, s, idx)
         units, metric, unit = len(idx), "gram_entries_per_sec", "entries/s"
-        cfg = {"workload": "c3: N=32 FermionicPQCKernel Gram, fp64", "pairs_per_step": int(len(idx))}
+        cfg = {"workload": WORKLOADS["c3"], "n_qubits": n, "pairs_per_step": int(len(idx))}
         sample = f"{len(idx)} Gram cells per step (full config: 33550336)"
     else:
         print(json.dumps({"impl": "reference", "unavailable": f"no CPU arm for workload {args.workload}"}))
@@ -220,8 +226,7 @@ def main():
 
         units_per_step = B * ws
         metric, unit, scaling = "circuit_expvals_per_sec", "expvals/s", "weak"
-        cfg = {"workload": "c2: N=16 README CompRxRx/RyRy/RzRz+fSWAP circuit, projector |0..0>, batch 65536 per GPU",
-               "n_qubits": n, "batch_per_gpu": B, "parallelism": f"batch sharded x{ws}, one all-gather of the outputs",
+        cfg = {"workload": WORKLOADS["c2"], "n_qubits": n, "batch_per_gpu": B, "parallelism": f"batch sharded x{ws}, one all-gather of the outputs",
                "l2": f"rotating pool of {len(pool)} input buffers ({len(pool) * B * 16 / 2**20:.0f} MiB > 126 MiB L2)"}
         kernel_name = "expval_warp_kernel<4>"
         alg_flops_per_launch = c2_flops_per_unit(n) * B
@@ -269,8 +274,7 @@ def main():
         units_per_step = entries
         e2e_units = entries
         metric, unit, scaling = "gram_entries_per_sec", "entries/s", "strong"
-        cfg = {"workload": "c3: N=32 FermionicPQCKernel(rotations='X,Z') Gram 8192x8192, 33550336 evaluated cells",
-               "n_qubits": n, "n_samples": ns, "parallelism": f"Gram rows sharded x{ws}, one all-gather",
+        cfg = {"workload": WORKLOADS["c3"], "n_qubits": n, "n_samples": ns, "parallelism": f"Gram rows sharded x{ws}, one all-gather",
                "l2": "per-sample covariances 268 MB > 126 MiB L2"}
         kernel_name = "gram_tiles_kernel<8,2,4>"
         alg_flops_per_launch = gram_flops_per_entry(2 * n) * entries / ws
@@ -299,8 +303,7 @@ def main():
         units_per_step = B * ws
         e2e_units = 0
         metric, unit, scaling = "marginal_distributions_per_sec", "distributions/s", "weak"
-        cfg = {"workload": "c4: N=64 depth-64 brickwork matchgate circuit, probs over 8 wires (256 outcomes), batch 16384 per GPU",
-               "n_qubits": n, "batch_per_gpu": B, "l2": "parameter tensor 528 MB > 126 MiB L2"}
+        cfg = {"workload": WORKLOADS["c4"], "n_qubits": n, "batch_per_gpu": B, "l2": "parameter tensor 528 MB > 126 MiB L2"}
         kernel_name = "circuit_columns_kernel"
         alg_flops_per_launch = len(gates) * 12 * (2 * k) * B
         launches_per_step = None
@@ -356,8 +359,13 @@ def main():
             # time the dominant kernel alone with events around a single launch of it
             kernel_ms = time_dominant_kernel(args.workload, locals())
         achieved = alg_flops_per_launch / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(TRAFFIC_FILE)).get(args.workload if ws == 1 else "", {}).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
         roofline = {"kernel": kernel_name, "bound": "fp64", "achieved": achieved, "peak": dfma, "unit": "TFLOP/s",
-                    "frac": achieved / dfma, "traffic": None,
+                    "frac": achieved / dfma, "traffic": traffic,
                     "peak_source": "in-run register-resident DFMA probe (MEASURED_PEAKS.json has no FP64 entry); "
                                    f"DMMA m8n8k4 probe = {dmma:.1f} TFLOP/s",
                     "avg_launch_ms": kernel_ms, "algorithmic_flops_per_launch": alg_flops_per_launch}
