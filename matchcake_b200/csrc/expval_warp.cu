@@ -259,7 +259,7 @@ int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long lon
   const int warps = 6;
   const int gates_in_smem = 1;
   const size_t gate_bytes = (((size_t)h->n_gates * 2 * sizeof(int)) + 15) & ~(size_t)15;
-  const size_t per_warp = ((((size_t)d * LDX + 128 + 6 * M) * sizeof(double) + 64) + 15) & ~(size_t)15;
+  const size_t per_warp = ((((size_t)d * LDX + 128 + (2 * M + 4 * (M + 8))) * sizeof(double) + 64) + 15) & ~(size_t)15;
   const size_t smem = gate_bytes + warps * per_warp;
   if (smem > (size_t)kMaxDynSmem) return -1;  // caller falls back to the block-per-instance kernel
   long long blocks = (B + warps - 1) / warps;

@@ -88,7 +88,7 @@ static int launch_tiles(const Src& src, long long n_items, int m, int out_mode, 
   const long long cap = 16LL * kNumSMs;
   if (blocks > cap) blocks = cap;
   auto go = [&](auto kernel, int mt) -> int {
-    const size_t smem = (size_t)warps * 6 * 8 * mt * sizeof(double);
+    const size_t smem = (size_t)warps * (2 * 8 * mt + 4 * (8 * mt + 8)) * sizeof(double);
     kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(src, n_items, m, out_mode, scale, out);
     return check_launch(what);
   };
@@ -160,13 +160,21 @@ struct GramTileArgs {
 };
 
 // One warp per (i, j) cell.  A block of TI x TJ warps walks (row-block, column-block) tiles so that the fragments
-// of the TI + TJ covariances it touches stay in L1.
-template <int MT, int TI, int TJ>
-__global__ void __launch_bounds__(32 * TI * TJ, 1) gram_tiles_kernel(GramTileArgs g) {
+// of the TI + TJ covariances it touches stay in L1.  SR tile-rows of the working matrix live in shared memory.
+template <int MT, int SR>
+struct GramSmem {
+  static constexpr int kSmTiles = SR > 0 ? Tiles<MT>::idx(SR - 1, MT - 1) + 1 : 0;     // tiles with ti < SR
+  static constexpr int kPerWarp = Tiles<MT>::kScratch + kSmTiles * 64;                  // doubles
+};
+
+template <int MT, int SR, int TI, int TJ, int MINB>
+__global__ void __launch_bounds__(32 * TI * TJ, MINB) gram_tiles_kernel(GramTileArgs g) {
   constexpr int NT = Tiles<MT>::NT;
-  extern __shared__ double smem[];
-  double* scratch = smem + (size_t)warp_id() * Tiles<MT>::kScratch;
+  constexpr int SMT = GramSmem<MT, SR>::kSmTiles;
+  extern __shared__ __align__(16) double smem[];
+  double* scratch = smem + (size_t)warp_id() * GramSmem<MT, SR>::kPerWarp;
   const int lane = lane_id();
+  double2* sm = reinterpret_cast<double2*>(scratch + Tiles<MT>::kScratch) + lane;
   const int wi = warp_id() / TJ, wj = warp_id() % TJ;
   const long long rows = g.row_end - g.row_begin;
   const long long rb_n = (rows + TI - 1) / TI, cb_n = (g.n1 + TJ - 1) / TJ;
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(32 * TI * TJ, 1) gram_tiles_kernel(GramTileArg
     const long long rb = t / cb_n, cb = t - rb * cb_n;
     const long long i_lo = g.row_begin + rb * TI, j_lo = cb * TJ;
     if (g.mode != MCB200_GRAM_FULL) {  // skip tiles that hold no evaluated cell (uniform over the block)
-      if (!upper && j_lo >= i_lo + TI - 1 + 1) continue;      // all j >= i
+      if (!upper && j_lo >= i_lo + TI) continue;              // all j >= i
       if (upper && j_lo + TJ - 1 <= i_lo) continue;           // all j <= i
     }
     const long long i = i_lo + wi, j = j_lo + wj;
@@ -188,10 +196,14 @@ __global__ void __launch_bounds__(32 * TI * TJ, 1) gram_tiles_kernel(GramTileArg
 #pragma unroll
     for (int q = 0; q < NT; ++q) {
       const double2 x = __ldg(a + q * 32), y = __ldg(b + q * 32);
-      c[q][0] = x.x + y.x;
-      c[q][1] = x.y + y.y;
+      if (q < SMT) {
+        sm[q * 32] = make_double2(x.x + y.x, x.y + y.y);
+      } else {
+        c[q][0] = x.x + y.x;
+        c[q][1] = x.y + y.y;
+      }
     }
-    const double pf = warp_pfaffian_tiles<MT>(c, g.m, scratch);
+    const double pf = warp_pfaffian_tiles<MT, SR>(c, g.m, scratch, sm);
     if (lane == 0) {
       const double v = g.scale * fabs(pf);
       g.K[i * g.ldk + j] = v;
@@ -225,13 +237,20 @@ static int gram_tiles_launch(const double* cov0, const double* cov1, long long n
   if (same) p1 = p0;
   else if (int rc = pack(cov1, n1, p1)) return rc;
   GramTileArgs g{p0, p1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk};
+  // 64 x 64: tile-rows 0 and 1 in shared memory -> <= 128 registers, two 8-warp blocks per SM (16 resident warps)
+  constexpr int SR = (MT >= 8) ? 2 : 0;
   constexpr int TI = 2, TJ = (MT >= 8) ? 4 : 8;
-  const size_t smem = (size_t)TI * TJ * Tiles<MT>::kScratch * sizeof(double);
+  constexpr int MINB = (MT >= 8) ? 2 : 1;
+  const size_t smem = (size_t)TI * TJ * GramSmem<MT, SR>::kPerWarp * sizeof(double);
   const long long rows = row_end - row_begin;
   const long long tiles = ((rows + TI - 1) / TI) * ((n1 + TJ - 1) / TJ);
-  const int per_sm = (MT >= 8) ? 1 : 2;
+  const int per_sm = 2;
   long long blocks = tiles < (long long)per_sm * kNumSMs ? tiles : (long long)per_sm * kNumSMs;
-  gram_tiles_kernel<MT, TI, TJ><<<(unsigned)blocks, 32 * TI * TJ, smem, st>>>(g);
+  auto kernel = gram_tiles_kernel<MT, SR, TI, TJ, MINB>;
+  if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                          "cudaFuncSetAttribute(gram_tiles)"))
+    return rc;
+  kernel<<<(unsigned)blocks, 32 * TI * TJ, smem, st>>>(g);
   return check_launch("gram_tiles_kernel");
 }
 

@@ -24,8 +24,10 @@ template <int MT>
 struct Tiles {
   static constexpr int NT = MT * (MT + 1) / 2;
   static constexpr int M = 8 * MT;
-  // scratch doubles per warp: rowbuf[M] | pbuf[M] | tau[M] | v[M] | negv[M] | zero[M]
-  static constexpr int kScratch = 6 * M;
+  // scratch doubles per warp: rowbuf[M] | pbuf[M] | 4 fragment vectors of M + 8 (the +8 shifts consecutive vectors
+  // by half a 128-byte bank line, so the two vectors read by one fragment load never collide)
+  static constexpr int kVec = M + 8;
+  static constexpr int kScratch = 2 * M + 4 * kVec;
   __host__ __device__ static constexpr int idx(int ti, int tj) { return ti * MT - (ti * (ti - 1)) / 2 + (tj - ti); }
 };
 
@@ -35,35 +37,67 @@ __device__ __forceinline__ void dmma_acc(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
-template <int MT, int TI>
-__device__ __forceinline__ void tiles_store_row(const double (&c)[Tiles<MT>::NT][2], double* row_st) {
-#pragma unroll
-  for (int tj = TI; tj < MT; ++tj)
-    *reinterpret_cast<double2*>(row_st + 8 * tj) =
-        make_double2(c[Tiles<MT>::idx(TI, tj)][0], c[Tiles<MT>::idx(TI, tj)][1]);
+// Tile access.  The first SR tile-rows (the ones that die first as the elimination proceeds) may live in shared
+// memory instead of registers -- fragment layout, sm[tile * 32] is this lane's (c0, c1) -- which cuts the register
+// footprint of a 64 x 64 matrix from 144 to 84 and doubles the number of resident warps.
+template <int MT, int SR, int TI, int TJ>
+__device__ __forceinline__ double2 tile_get(const double (&c)[Tiles<MT>::NT][2], const double2* sm) {
+  if constexpr (TI < SR) return sm[Tiles<MT>::idx(TI, TJ) * 32];
+  else return make_double2(c[Tiles<MT>::idx(TI, TJ)][0], c[Tiles<MT>::idx(TI, TJ)][1]);
 }
 
-template <int MT, int TI>
-__device__ __forceinline__ void tiles_store_row_right(const double (&c)[Tiles<MT>::NT][2], double* row_st) {
-#pragma unroll
-  for (int tj = TI + 1; tj < MT; ++tj)
-    *reinterpret_cast<double2*>(row_st + 8 * tj) =
-        make_double2(c[Tiles<MT>::idx(TI, tj)][0], c[Tiles<MT>::idx(TI, tj)][1]);
+template <int MT, int SR, int TI, int TJ0 = TI>
+__device__ __forceinline__ void tiles_store_row(const double (&c)[Tiles<MT>::NT][2], const double2* sm, double* row_st) {
+  if constexpr (TJ0 < MT) {
+    *reinterpret_cast<double2*>(row_st + 8 * TJ0) = tile_get<MT, SR, TI, TJ0>(c, sm);
+    tiles_store_row<MT, SR, TI, TJ0 + 1>(c, sm, row_st);
+  }
 }
 
-template <int MT, int TJ>
-__device__ __forceinline__ void tiles_store_col(const double (&c)[Tiles<MT>::NT][2], double* col_st, int e) {
-#pragma unroll
-  for (int ti = 0; ti <= TJ; ++ti) col_st[8 * ti] = e ? c[Tiles<MT>::idx(ti, TJ)][1] : c[Tiles<MT>::idx(ti, TJ)][0];
+template <int MT, int SR, int TI>
+__device__ __forceinline__ void tiles_store_row_right(const double (&c)[Tiles<MT>::NT][2], const double2* sm,
+                                                      double* row_st) {
+  tiles_store_row<MT, SR, TI, TI + 1>(c, sm, row_st);
 }
 
-template <int MT, int TI>
-__device__ __forceinline__ void tiles_update_from(double (&c)[Tiles<MT>::NT][2], const double (&af)[MT],
+template <int MT, int SR, int TJ, int TI0 = 0>
+__device__ __forceinline__ void tiles_store_col(const double (&c)[Tiles<MT>::NT][2], const double2* sm, double* col_st,
+                                                int e) {
+  if constexpr (TI0 <= TJ) {
+    const double2 v = tile_get<MT, SR, TI0, TJ>(c, sm);
+    col_st[8 * TI0] = e ? v.y : v.x;
+    tiles_store_col<MT, SR, TJ, TI0 + 1>(c, sm, col_st, e);
+  }
+}
+
+template <int MT, int SR, int TI, int TJ>
+__device__ __forceinline__ void tile_update(double (&c)[Tiles<MT>::NT][2], double2* sm, double a, double b) {
+  if constexpr (TI < SR) {
+    const double2 v = sm[Tiles<MT>::idx(TI, TJ) * 32];
+    double t[2] = {v.x, v.y};
+    dmma_acc(t, a, b);
+    sm[Tiles<MT>::idx(TI, TJ) * 32] = make_double2(t[0], t[1]);
+  } else {
+    dmma_acc(c[Tiles<MT>::idx(TI, TJ)], a, b);
+  }
+}
+
+template <int MT, int SR, int TI, int TJ>
+__device__ __forceinline__ void tiles_update_row(double (&c)[Tiles<MT>::NT][2], double2* sm, const double (&af)[MT],
+                                                 const double (&bf)[MT]) {
+  if constexpr (TJ < MT) {
+    tile_update<MT, SR, TI, TJ>(c, sm, af[TI], bf[TJ]);
+    tiles_update_row<MT, SR, TI, TJ + 1>(c, sm, af, bf);
+  }
+}
+
+template <int MT, int SR, int TI>
+__device__ __forceinline__ void tiles_update_from(double (&c)[Tiles<MT>::NT][2], double2* sm, const double (&af)[MT],
                                                   const double (&bf)[MT]) {
-#pragma unroll
-  for (int ti = TI; ti < MT; ++ti)
-#pragma unroll
-    for (int tj = ti; tj < MT; ++tj) dmma_acc(c[Tiles<MT>::idx(ti, tj)], af[ti], bf[tj]);
+  if constexpr (TI < MT) {
+    tiles_update_row<MT, SR, TI, TI>(c, sm, af, bf);
+    tiles_update_from<MT, SR, TI + 1>(c, sm, af, bf);
+  }
 }
 
 #define MCB200_TILE_SWITCH(var, MTv, CALL)            \
@@ -78,10 +112,11 @@ __device__ __forceinline__ void tiles_update_from(double (&c)[Tiles<MT>::NT][2],
     default: { constexpr int K_ = 7; if constexpr (K_ < MTv) { CALL; } } break; \
   }
 
-// c: fragments of the upper tiles (entries at rows/cols >= m must be 0).  scratch: Tiles<MT>::kScratch doubles
-// private to the warp.  Returns the signed Pfaffian in every lane.
-template <int MT>
-__device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, double* scratch) {
+// c: fragments of the upper tiles (entries at rows/cols >= m must be 0); with SR > 0 the tiles of the first SR
+// tile-rows are read from / written to sm (this lane's slot, see tile_get) instead.  scratch: Tiles<MT>::kScratch
+// doubles private to the warp.  Returns the signed Pfaffian in every lane.
+template <int MT, int SR = 0>
+__device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, double* scratch, double2* sm = nullptr) {
   using T = Tiles<MT>;
   constexpr int H = (T::M + 31) / 32;  // vector entries / pivot candidates per lane
   const int lane = lane_id(), gr = lane >> 2, tg = lane & 3;
@@ -89,20 +124,20 @@ __device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, doub
   if (m & 1) return 0.0;
   double* rowbuf = scratch;
   double* pbuf = scratch + T::M;
-  double* tauv = scratch + 2 * T::M;
-  double* vv = scratch + 3 * T::M;
-  double* negv = scratch + 4 * T::M;
-  double* zero = scratch + 5 * T::M;
-#pragma unroll
-  for (int h = 0; h < H; ++h)
-    if (lane + 32 * h < T::M) zero[lane + 32 * h] = 0.0;
+  // fragment vectors.  The rank-2 update A += tau v^T - v tau^T is issued as a K = 4 DMMA with
+  //   A-fragment columns (tau/2, -v/2, tau/2, -v/2)  and  B-fragment rows (v; tau; v; tau),
+  // so that every lane reads one of two vectors per fragment (even / odd tg) and the two 64-byte groups of a
+  // fragment load fall into different halves of the 128-byte bank line (conflict free, broadcast within a group).
+  double* tauh = scratch + 2 * T::M;          // tau / 2      (A, even tg)
+  double* negvh = tauh + T::kVec;             // -v / 2       (A, odd tg)
+  double* vv = negvh + T::kVec;               // v            (B, even tg)
+  double* tauv = vv + T::kVec;                // tau          (B, odd tg)
   // per-lane store / load addresses (loop invariant)
   double* row_st = rowbuf + 2 * tg;   // row r -> rowbuf[8 tj + 2 tg .. +1]
   double* prow_st = pbuf + 2 * tg;    // row p -> pbuf[8 tj + 2 tg .. +1]
   double* pcol_st = pbuf + gr;        // column p -> pbuf[8 ti + gr]
-  // fragment sources, fixed per lane: A-fragment column tg = (tau, -v, 0, 0), B-fragment row tg = (v; tau; 0; 0)
-  const double* srcA = ((tg == 0) ? tauv : (tg == 1) ? negv : zero) + gr;
-  const double* srcB = ((tg == 0) ? vv : (tg == 1) ? tauv : zero) + gr;
+  const double* srcA = ((tg & 1) ? negvh : tauh) + gr;
+  const double* srcB = ((tg & 1) ? tauv : vv) + gr;
   // active set as two 32-bit words (uniform) + this lane's own entries j = lane, lane + 32
   unsigned act_lo = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
   unsigned act_hi = (m >= 64) ? 0xffffffffu : ((m > 32) ? ((1u << (m - 32)) - 1u) : 0u);
@@ -116,7 +151,7 @@ __device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, doub
     const int tr = r >> 3;
     // (1) row r, columns in tile-columns >= tr
     if (gr == (r & 7)) {
-      MCB200_TILE_SWITCH(tr, MT, (tiles_store_row<MT, K_>(c, row_st)))
+      MCB200_TILE_SWITCH(tr, MT, (tiles_store_row<MT, SR, K_>(c, sm, row_st)))
     }
     if (lane == (r & 31)) {  // r leaves the active set before the search
       if (r < 32) on0 = false; else on1 = false;
@@ -140,10 +175,10 @@ __device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, doub
     const double piv = rowbuf[p];
     // (3) v_j = A[j][p]: column p of the tiles above/at the diagonal; row p (NOT negated here) to the right
     if (tg == ((p & 7) >> 1)) {
-      MCB200_TILE_SWITCH(tp, MT, (tiles_store_col<MT, K_>(c, pcol_st, p & 1)))
+      MCB200_TILE_SWITCH(tp, MT, (tiles_store_col<MT, SR, K_>(c, sm, pcol_st, p & 1)))
     }
     if (gr == (p & 7)) {
-      MCB200_TILE_SWITCH(tp, MT, (tiles_store_row_right<MT, K_>(c, prow_st)))
+      MCB200_TILE_SWITCH(tp, MT, (tiles_store_row_right<MT, SR, K_>(c, sm, prow_st)))
     }
     if (lane == (p & 31)) {
       if (p < 32) on0 = false; else on1 = false;
@@ -166,9 +201,10 @@ __device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, doub
       double v0 = on0 ? pbuf[lane] : 0.0;
       if ((lane >> 3) > tp) v0 = -v0;
       if (lane < T::M) {
-        tauv[lane] = t0;
+        tauh[lane] = 0.5 * t0;
+        negvh[lane] = -0.5 * v0;
         vv[lane] = v0;
-        negv[lane] = -v0;
+        tauv[lane] = t0;
       }
       if (H > 1) {
         const int j = j1;
@@ -176,9 +212,10 @@ __device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, doub
         double v1 = on1 ? pbuf[j] : 0.0;
         if ((j >> 3) > tp) v1 = -v1;
         if (lane + 32 < T::M) {
-          tauv[j] = t1;
+          tauh[j] = 0.5 * t1;
+          negvh[j] = -0.5 * v1;
           vv[j] = v1;
-          negv[j] = -v1;
+          tauv[j] = t1;
         }
       }
     }
@@ -190,7 +227,7 @@ __device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, doub
       bf[t] = srcB[8 * t];
     }
     // (5) rank-2 update on the tensor pipe: one DMMA per live upper tile
-    MCB200_TILE_SWITCH(tr, MT, (tiles_update_from<MT, K_>(c, af, bf)))
+    MCB200_TILE_SWITCH(tr, MT, (tiles_update_from<MT, SR, K_>(c, sm, af, bf)))
     __syncwarp();
   }
   return (parity & 1u) ? -pf : pf;
