@@ -32,6 +32,7 @@ L2_BYTES = 126 * 1024 * 1024
 WORKLOADS = {
     "c2": "c2: N=16 README CompRxRx/RyRy/RzRz+fSWAP circuit, projector |0..0> expval, batch 65536 per GPU (BASELINE configs[1])",
     "c3": "c3: N=32 FermionicPQCKernel(rotations='X,Z') Gram 8192x8192, 33550336 evaluated cells (BASELINE configs[2])",
+    "c5": "c5: N=128 FermionicPQCKernel Nystroem Gram: 4096 landmarks (K_mm) + 262144 samples x 4096 landmarks (transform), 1073737728 evaluated cells (BASELINE configs[4])",
     "c4": "c4: N=64 depth-64 brickwork matchgate circuit, probs over 8 wires (256 outcomes), batch 16384 per GPU (BASELINE configs[3])",
 }
 # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r01/ncu_*.txt)
@@ -168,11 +169,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    defaults = {"c2": (200, 10), "c3": (3, 3), "c4": (20, 3)}[args.workload]
+    defaults = {"c2": (200, 10), "c3": (3, 3), "c4": (20, 3), "c5": (3, 3)}[args.workload]
     args.steps = args.steps if args.steps is not None else defaults[0]
     args.warmup = max(3, args.warmup if args.warmup is not None else defaults[1])
     if args.impl == "reference":
@@ -280,6 +281,36 @@ def main():
         alg_flops_per_launch = gram_flops_per_entry(2 * n) * entries / ws
         launches_per_step = None
         h2d, d2h = ns * 2 * n * 8, ns * ns * 8
+    elif args.workload == "c5":
+        from matchcake_b200.ml.kernels import FermionicPQCKernel
+
+        n, ns, nl = 128, 262144, 4096
+        x = np.random.default_rng(0).random((ns, n))  # depth_ = 1: 64 independent wire pairs (block-diagonal SPTM)
+        kern = FermionicPQCKernel(n_qubits=n, rotations="X,Z", r_dtype=torch.float64, c_dtype=torch.complex128)
+        kern.float32_gram = False
+        kern.fit(x[:8])
+        from sklearn.utils import check_random_state
+
+        basis = x[check_random_state(0).permutation(ns)[:nl]]  # nystroem.py:88-91
+        x_dev, basis_dev = torch.as_tensor(x).to(dev), torch.as_tensor(basis).to(dev)
+
+        def step(i):
+            kmm = kern(basis_dev)               # Nystroem.fit: square landmark Gram
+            return kern(x_dev, basis_dev)       # Nystroem.transform: rectangular Gram (reference triangle rules)
+
+        e2e_step = None
+        entries = nl * (nl - 1) // 2 + ns * nl - nl * (nl + 1) // 2
+        units_per_step = entries
+        e2e_units = 0
+        metric, unit, scaling = "gram_entries_per_sec", "entries/s", "strong"
+        cfg = {"workload": WORKLOADS["c5"], "n_qubits": n, "n_samples": ns, "n_landmarks": nl,
+               "parallelism": f"Gram rows sharded x{ws}, one all-gather",
+               "algorithm": "depth_=1 ansatz => 64 independent wire pairs: K_ij = prod_c 2^-2 |Pf_4| (gram_blocks4_kernel)",
+               "l2": "per-sample block data 805 MB + Gram 8.6 GB > 126 MiB L2"}
+        kernel_name = "gram_blocks4_kernel"
+        alg_flops_per_launch = 64 * 12.0 * (ns * nl - nl * (nl + 1) // 2) / ws
+        launches_per_step = None
+        h2d, d2h = 0, 0
     else:  # c4
         n, B, depth, k = 64, 16384, 64, 8
         gates = []
@@ -422,7 +453,16 @@ def time_dominant_kernel(workload, env):
 
     from matchcake_b200 import ops as mops
 
-    if workload == "c3":
+    if workload == "c5":
+        kern, x_dev, basis_dev, ws = env["kern"], env["x_dev"], env["basis_dev"], env["ws"]
+        from matchcake_b200 import distributed as dm
+
+        b0, b1 = kern._x_to_blocks(x_dev), kern._x_to_blocks(basis_dev)
+        s, e = dm.balanced_row_ranges(b0.shape[0], b1.shape[0], ws)[0]
+        out = torch.zeros((b0.shape[0], b1.shape[0]), dtype=torch.float64, device=b0.device)
+        fn = lambda: mops.gram_blocks4(b0, b1, mode=mops.GRAM_TRIANGLE if ws > 1 else mops.GRAM_REFERENCE,
+                                       row_range=(s, e), out=out)
+    elif workload == "c3":
         kern, x_dev, ws = env["kern"], env["x_dev"], env["ws"]
         cov = kern._x_to_cov(x_dev)
         from matchcake_b200 import distributed as dm

@@ -167,6 +167,22 @@ int mcb200_gram(const double* cov0, const double* cov1, int64_t n0, int64_t n1, 
                 int64_t row_begin, int64_t row_end, int32_t mode, double scale, double* K,
                 int64_t ldk, void* workspace, void* stream);
 
+/* Gram for circuits whose wires split into C independent 2-qubit groups (block-diagonal SPTM, e.g.
+ * FermionicPQCKernel with depth_ = 1, fermionic_pqc_kernel.py:183-192): blocks (n, C, 6) hold the upper triangles
+ * (01,02,03,12,13,23) of the 4x4 diagonal blocks of the per-sample covariances and
+ * K[i, j] = scale * prod_c |Pf_4(blocks0[i, c] + blocks1[j, c])|  (scale = 2^-2C).  Same modes / row range as mcb200_gram. */
+int mcb200_gram_blocks4(const double* blocks0, const double* blocks1, int64_t n0, int64_t n1, int32_t C,
+                        int64_t row_begin, int64_t row_end, int32_t mode, double scale, double* K, int64_t ldk,
+                        void* stream);
+
+/* Input of mcb200_gram_blocks4 straight from the circuit: for every instance b and wire pair (pair_wire0[c],
+ * pair_wire0[c] + 1) the 6 upper-triangular entries of the pair's 4x4 covariance block, blocks_out (B, C, 6).
+ * Only the gates whose wire0 equals pair_wire0[c] act on pair c (the caller guarantees that no gate couples two
+ * pairs).  Replaces NIFKernel._x_to_sptm + covariance_matrix for block-diagonal circuits. */
+int mcb200_circuit_pair_blocks(const mcb200_circuit_t* circuit_host, const double* params, int64_t B,
+                               const int32_t* pair_wire0, int32_t C, const int8_t* init_bits,
+                               double* blocks_out, void* stream);
+
 /* GramMatrix.symmetrize_ + _fill_diagonal_ (gram_matrix.py:127-161) on a device (n0, n1) matrix. */
 int mcb200_gram_symmetrize(double* K, int64_t n0, int64_t n1, int64_t ldk, void* stream);
 

@@ -54,6 +54,8 @@ SIGNATURES = {
     "mcb200_circuit_expval_projector": (c_i32, [C.POINTER(CircuitStruct), c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "mcb200_gram_workspace_bytes": (c_i64, [c_i64, c_i64, c_i32]),
     "mcb200_gram": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i64, c_i64, c_i32, c_f64, c_vp, c_i64, c_vp, c_vp]),
+    "mcb200_circuit_pair_blocks": (c_i32, [C.POINTER(CircuitStruct), c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "mcb200_gram_blocks4": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i64, c_i64, c_i32, c_f64, c_vp, c_i64, c_vp]),
     "mcb200_gram_symmetrize": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp]),
     "mcb200_launch_count": (c_i64, []),
     "mcb200_reset_launch_count": (None, []),

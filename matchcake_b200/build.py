@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcb200.so")
-SOURCES = ["api.cu", "circuit.cu", "pfaffian.cu", "pfaffian_tiles.cu", "expval_warp.cu", "gemm.cu"]
+SOURCES = ["api.cu", "circuit.cu", "pfaffian.cu", "pfaffian_tiles.cu", "expval_warp.cu", "gram_blocks.cu", "gemm.cu"]
 HEADERS = ["common.cuh", "pfaffian_dev.cuh", "pfaffian_tiles.cuh", "tiles_api.cuh", os.path.join("..", "..", "include", "mcb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -67,4 +67,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    try:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    except RuntimeError as e:  # make a failed build impossible to miss behind `| tail`
+        print(str(e)[-3000:])
+        print("BUILD FAILED")
+        sys.exit(1)

@@ -289,6 +289,80 @@ __global__ void circuit_expval_projector_kernel(CircuitDev c, const double* __re
   if (threadIdx.x == 0) out[b] = ldexp(fabs(pf), -n);
 }
 
+// Block-diagonal circuits: one THREAD per (instance, wire pair).  The pair's 4x4 SPTM block is built in registers
+// from the gates that act on it (reverse application order, left multiplication), then its covariance block
+// Lambda^(c) = X^T Lambda_0^(c) X is written as the 6 upper-triangular entries (01,02,03,12,13,23).
+__global__ void __launch_bounds__(256) circuit_pair_blocks_kernel(CircuitDev c, const double* __restrict__ params,
+                                                                  long long B, const int32_t* __restrict__ pair_wire0,
+                                                                  int C, const int8_t* init_bits,
+                                                                  double* __restrict__ out) {
+  extern __shared__ mcb200_gate_t sgates[];
+  for (int i = threadIdx.x; i < c.n_gates * 6; i += blockDim.x)
+    reinterpret_cast<int32_t*>(sgates)[i] = reinterpret_cast<const int32_t*>(c.gates)[i];
+  __syncthreads();
+  const long long total = B * C;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / C;
+    const int pc = (int)(e - b * C);
+    const int w0 = pair_wire0[pc];
+    const double* prow = params + b * c.n_param_cols;
+    double x[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int gi = c.n_gates - 1; gi >= 0; --gi) {
+      const mcb200_gate_t g = sgates[gi];
+      if (g.wire0 != w0) continue;
+      if (g.kind <= MCB200_GATE_RZRZ) {
+        double cf[4];
+        gate_coefficients(c, g, prow, cf);
+        // row pairs (i0, i1), (j0, j1): RXRX (0,3),(1,2); RYRY (0,2),(1,3); RZRZ (0,1),(2,3)
+#pragma unroll
+        for (int col = 0; col < 4; ++col) {
+          const double x0 = x[0][col], x1 = x[1][col], x2 = x[2][col], x3 = x[3][col];
+          if (g.kind == MCB200_GATE_RXRX) {
+            x[0][col] = cf[0] * x0 + cf[1] * x3;  x[3][col] = cf[0] * x3 - cf[1] * x0;
+            x[1][col] = cf[2] * x1 + cf[3] * x2;  x[2][col] = cf[2] * x2 - cf[3] * x1;
+          } else if (g.kind == MCB200_GATE_RYRY) {
+            x[0][col] = cf[0] * x0 + cf[1] * x2;  x[2][col] = cf[0] * x2 - cf[1] * x0;
+            x[1][col] = cf[2] * x1 + cf[3] * x3;  x[3][col] = cf[2] * x3 - cf[3] * x1;
+          } else {
+            x[0][col] = cf[0] * x0 + cf[1] * x1;  x[1][col] = cf[0] * x1 - cf[1] * x0;
+            x[2][col] = cf[2] * x2 + cf[3] * x3;  x[3][col] = cf[2] * x3 - cf[3] * x2;
+          }
+        }
+      } else if (g.kind == MCB200_GATE_FSWAP) {  // adjacent fSWAP: rows (0,1) <-> (2,3)
+#pragma unroll
+        for (int col = 0; col < 4; ++col) {
+          const double x0 = x[0][col], x1 = x[1][col];
+          x[0][col] = x[2][col];  x[1][col] = x[3][col];  x[2][col] = x0;  x[3][col] = x1;
+        }
+      } else {
+        const double* m4 = (g.kind == MCB200_GATE_BLOCK4_CONST) ? c.consts + g.off : prow + g.off;
+        const bool tr = g.flags & MCB200_GATE_FLAG_TRANSPOSE;
+#pragma unroll
+        for (int col = 0; col < 4; ++col) {
+          const double x0 = x[0][col], x1 = x[1][col], x2 = x[2][col], x3 = x[3][col];
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            x[a][col] = (tr ? m4[a] : m4[4 * a]) * x0 + (tr ? m4[4 + a] : m4[4 * a + 1]) * x1 +
+                        (tr ? m4[8 + a] : m4[4 * a + 2]) * x2 + (tr ? m4[12 + a] : m4[4 * a + 3]) * x3;
+        }
+      }
+    }
+    const double s0 = (init_bits != nullptr && init_bits[w0]) ? 1.0 : -1.0;
+    const double s1 = (init_bits != nullptr && init_bits[w0 + 1]) ? 1.0 : -1.0;
+    double* o = out + e * 6;
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b2 = a + 1; b2 < 4; ++b2)
+        o[q++] = s0 * (x[0][a] * x[1][b2] - x[1][a] * x[0][b2]) + s1 * (x[2][a] * x[3][b2] - x[3][a] * x[2][b2]);
+  }
+}
+
 }  // namespace mcb200
 
 // ---------------------------------------------------------------------------------------------- C ABI
@@ -388,4 +462,25 @@ extern "C" int mcb200_circuit_expval_projector(const mcb200_circuit_t* circuit_h
   circuit_expval_projector_kernel<<<(unsigned)B, threads, smem, as_stream(stream)>>>(c, params, init_bits,
                                                                                    target_bits, out);
   return check_launch("circuit_expval_projector_kernel");
+}
+
+extern "C" int mcb200_circuit_pair_blocks(const mcb200_circuit_t* circuit_host, const double* params, int64_t B,
+                                          const int32_t* pair_wire0, int32_t C, const int8_t* init_bits,
+                                          double* blocks_out, void* stream) {
+  CircuitDev c;
+  if (int rc = circuit_to_dev(circuit_host, &c)) return rc;
+  if (B < 0 || C < 0) return set_error("circuit_pair_blocks: negative size");
+  if (B == 0 || C == 0) return 0;
+  if (pair_wire0 == nullptr || blocks_out == nullptr) return set_error("circuit_pair_blocks: NULL pointer");
+  if (c.n_param_cols > 0 && params == nullptr) return set_error("params is NULL");
+  const size_t smem = (size_t)c.n_gates * sizeof(mcb200_gate_t);
+  if (smem > 96 * 1024) return set_error("circuit_pair_blocks: %d gates exceed the shared-memory gate table", c.n_gates);
+  if (int rc = check_cuda(cudaFuncSetAttribute(circuit_pair_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem), "cudaFuncSetAttribute(circuit_pair_blocks)"))
+    return rc;
+  long long blocks = (B * C + 255) / 256;
+  if (blocks > 64LL * kNumSMs) blocks = 64LL * kNumSMs;
+  circuit_pair_blocks_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(c, params, B, pair_wire0, C, init_bits,
+                                                                               blocks_out);
+  return check_launch("circuit_pair_blocks_kernel");
 }

@@ -49,6 +49,7 @@ class FermionicPQCKernel(NIFKernel):
         self.bias_: Optional[np.ndarray] = None
         self.data_scaling_: Optional[np.ndarray] = None
         self._circuit = None
+        self._plan = None
 
     def fit(self, x_train, y_train=None):
         x_arr = x_train.detach().cpu().numpy() if isinstance(x_train, torch.Tensor) else np.asarray(x_train)
@@ -58,7 +59,9 @@ class FermionicPQCKernel(NIFKernel):
         if self.depth_ is None:
             self.depth_ = int(max(1, np.ceil(x_arr.shape[-1] / self.n_qubits)))
         self._circuit = None
+        self._plan = None
         self._covs_train = None
+        self._blocks_train = None
         super().fit(x_train, y_train)
         return self
 
@@ -112,6 +115,7 @@ class FermionicPQCKernel(NIFKernel):
         identity = len(idx) == f and np.array_equal(idx, np.arange(f))
         circ = _ops.CompiledCircuit(nq, gates, len(idx), scale=scale, bias=bias,
                                     consts=np.asarray(consts) if consts else None)
+        self._compiled_host = (gates, scale, bias, consts)
         self._circuit = (circ, None if identity else torch.as_tensor(idx, device="cuda"))
         return self._circuit
 
@@ -126,3 +130,36 @@ class FermionicPQCKernel(NIFKernel):
 
     def _x_to_sptm(self, x) -> torch.Tensor:
         return _ops.circuit_columns(self._compiled()[0], self._features(x))
+
+    # ------------------------------------------------------------------ independent wire pairs (block-diagonal SPTM)
+    def _block_plan(self):
+        """If no gate couples two different wire pairs (depth_ = 1: rotations and entanglers act on the same pairs,
+        fermionic_pqc_kernel.py:183-192) return one 2-qubit sub-circuit per pair; else None."""
+        if self._plan is not None:
+            return self._plan if self._plan is not False else None
+        self._compiled()
+        gates, scale, bias, consts = self._compiled_host
+        parent = list(range(self.n_qubits))
+
+        def find(a):
+            while parent[a] != a:
+                parent[a] = parent[parent[a]]
+                a = parent[a]
+            return a
+
+        for g in gates:
+            for w in range(g.wire0, g.wire1):
+                parent[find(w)] = find(w + 1)
+        comps = {}
+        for g in gates:
+            comps.setdefault(find(g.wire0), set()).update(range(g.wire0, g.wire1 + 1))
+        comps = sorted(sorted(c) for c in comps.values())
+        if len(comps) < 2 or any(len(c) != 2 or c[1] != c[0] + 1 for c in comps):
+            self._plan = False
+            return None
+        self._plan = torch.as_tensor([c[0] for c in comps], dtype=torch.int32, device="cuda")
+        return self._plan
+
+    def _x_to_blocks(self, x) -> torch.Tensor:
+        """(n_samples, n_pairs, 6): upper triangles of the 4x4 diagonal blocks of the per-sample covariances."""
+        return _ops.circuit_pair_blocks(self._compiled()[0], self._features(x), self._block_plan())

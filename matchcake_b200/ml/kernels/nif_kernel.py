@@ -43,6 +43,10 @@ class NIFKernel(Kernel):
         self._covs_train = None
         #: store the Gram in float32 like the reference's GramMatrix (gram_matrix.py:38-47); False keeps float64
         self.float32_gram = True
+        #: when the ansatz never couples different wire pairs the covariance is block diagonal (4x4 blocks) and the
+        #: Gram factorises into 2-qubit factors (csrc/gram_blocks.cu); False forces the dense Pfaffian path
+        self.use_block_factorisation = True
+        self._blocks_train = None
 
     # sklearn's get_params reads attributes named like the __init__ arguments
     @property
@@ -117,8 +121,28 @@ class NIFKernel(Kernel):
             self._covs_train = (self.x_train_, self._x_to_cov(self.x_train_))
         return self._covs_train[1]
 
+    def _block_plan(self):
+        """Sub-circuits per independent wire pair, or None (subclasses with a compiled ansatz override this)."""
+        return None
+
+    def _x_to_blocks(self, x) -> torch.Tensor:
+        raise NotImplementedError
+
     def compute_similarities(self, x0, x1, **kwargs) -> torch.Tensor:
         same = x1 is x0
+        full = kwargs.get("full_rectangle", False)
+        if self.use_block_factorisation and self._block_plan() is not None:
+            b0 = self._x_to_blocks(x0)
+            if kwargs.get("x1_train", False):
+                if self._blocks_train is None or self._blocks_train[0] is not self.x_train_:
+                    self._blocks_train = (self.x_train_, self._x_to_blocks(self.x_train_))
+                b1 = self._blocks_train[1]
+            else:
+                b1 = b0 if same else self._x_to_blocks(x1)
+            k = self.gram_from_blocks(b0, b1, full=full)
+            if self.float32_gram:
+                k = k.to(torch.float32)
+            return k.to(self.R_DTYPE)
         cov0 = self._x_to_cov(x0)
         if kwargs.get("x1_train", False):
             cov1 = self.covs_train
@@ -140,6 +164,22 @@ class NIFKernel(Kernel):
         def rows(s, e):
             out = torch.zeros((n0, n1), dtype=torch.float64, device=cov0.device)
             _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_TRIANGLE, row_range=(s, e), out=out)
+            return out[s:e]
+
+        k = dist_mod.sharded_rows(rows, ranges, n0)
+        return k if full else _ops.gram_symmetrize(k)
+
+    def gram_from_blocks(self, b0: torch.Tensor, b1: torch.Tensor, full: bool = False) -> torch.Tensor:
+        """Same contract as :meth:`gram_from_covariances` for block-diagonal covariances given as (n, C, 6)."""
+        n0, n1 = b0.shape[0], b1.shape[0]
+        rank, ws = dist_mod.world()
+        if ws == 1:
+            return _ops.gram_blocks4(b0, b1, mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE)
+        ranges = dist_mod.balanced_row_ranges(n0, n1, ws, full=full)
+
+        def rows(s, e):
+            out = torch.zeros((n0, n1), dtype=torch.float64, device=b0.device)
+            _ops.gram_blocks4(b0, b1, mode=_ops.GRAM_FULL if full else _ops.GRAM_TRIANGLE, row_range=(s, e), out=out)
             return out[s:e]
 
         k = dist_mod.sharded_rows(rows, ranges, n0)

@@ -296,6 +296,35 @@ def gram(cov0: torch.Tensor, cov1: torch.Tensor, scale: float, mode: int = GRAM_
     return out
 
 
+def circuit_pair_blocks(circ: CompiledCircuit, params: torch.Tensor, pair_wire0: torch.Tensor,
+                        init_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B, C, 6) covariance blocks of a circuit whose wire pairs (w, w+1), w in ``pair_wire0``, never interact."""
+    params = circ._params(params)
+    B = params.shape[0]
+    pw = pair_wire0.to(device=params.device, dtype=torch.int32).contiguous()
+    ib = None if init_bits is None else init_bits.to(device=params.device, dtype=torch.int8).contiguous()
+    out = torch.empty((B, pw.numel(), 6), dtype=torch.float64, device=params.device)
+    check(_lib.load().mcb200_circuit_pair_blocks(C.byref(circ._struct), _ptr(params), B, _ptr(pw), pw.numel(), _ptr(ib),
+                                                 _ptr(out), _stream()))
+    return out
+
+
+def gram_blocks4(blocks0: torch.Tensor, blocks1: torch.Tensor, mode: int = GRAM_REFERENCE,
+                 row_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gram of block-diagonal covariances: blocks (n, C, 6) = upper triangles of the C 4x4 diagonal blocks."""
+    blocks0, blocks1 = _f64(blocks0, "blocks0"), _f64(blocks1, "blocks1")
+    n0, C, six = blocks0.shape
+    n1 = blocks1.shape[0]
+    if six != 6 or blocks1.shape[1:] != (C, 6):
+        raise ValueError("blocks must be (n, C, 6)")
+    rb, re = (0, n0) if row_range is None else row_range
+    if out is None:
+        out = torch.zeros((n0, n1), dtype=torch.float64, device=blocks0.device)
+    check(_lib.load().mcb200_gram_blocks4(_ptr(blocks0), _ptr(blocks1), n0, n1, C, rb, re, mode, 2.0 ** (-2 * C),
+                                          _ptr(out), out.stride(0), _stream()))
+    return out
+
+
 def gram_symmetrize(k: torch.Tensor) -> torch.Tensor:
     check(_lib.load().mcb200_gram_symmetrize(_ptr(k), k.shape[0], k.shape[1], k.stride(0), _stream()))
     return k

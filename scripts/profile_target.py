@@ -40,6 +40,12 @@ elif what == "c4":
     for _ in range(2):
         x = mops.circuit_columns(circ, params, maj)
         out = mops.probs_all(mops.cov_basis(x, n), normalize=True)
+elif what == "blocks":
+    n = size or 32768
+    b0 = torch.randn(n, 64, 6, dtype=torch.float64, device=dev)
+    b1 = torch.randn(4096, 64, 6, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        out = mops.gram_blocks4(b0, b1)
 elif what == "pf":
     m = size or 64
     a = torch.randn(20000, m, m, dtype=torch.float64, device=dev)

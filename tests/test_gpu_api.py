@@ -250,3 +250,27 @@ def test_utils_pfaffian_namespace():
     a = rng.random((3, 4, 4))
     a = a - np.swapaxes(a, -1, -2)
     np.testing.assert_allclose(utils.pfaffian(a) ** 2, np.abs(np.linalg.det(a)), rtol=1e-10)
+
+
+@pytest.mark.parametrize("n,nf,rot,ent", [(8, 8, "X,Z", "fswap"), (6, 5, "Y,Z", "fswap"), (10, 10, "X", "identity"),
+                                          (4, 4, "Z,Y,X", "hadamard")])
+def test_block_factorised_gram_equals_dense_and_oracle(n, nf, rot, ent):
+    """depth_ = 1 ansatz: the SPTM is block diagonal and the Gram factorises into 2-qubit factors (gram_blocks.cu)."""
+    rng = np.random.default_rng(n * 7 + nf)
+    x0, x1 = rng.random((70, nf)), rng.random((9, nf))
+    k = FermionicPQCKernel(n_qubits=n, rotations=rot, entangling_mth=ent, r_dtype=torch.float64, c_dtype=torch.complex128)
+    k.float32_gram = False
+    k.fit(x0)
+    assert k.depth_ == 1 and k._block_plan() is not None
+    fast = [k(x0).cpu().numpy(), k(x0, x1).cpu().numpy(), k(x1, x0).cpu().numpy(), k.transform(x1)]
+    k.use_block_factorisation = False
+    dense = [k(x0).cpu().numpy(), k(x0, x1).cpu().numpy(), k(x1, x0).cpu().numpy(), k.transform(x1)]
+    for a, b in zip(fast, dense):
+        np.testing.assert_allclose(a, b, rtol=RTOL, atol=ATOL)
+    if ent != "hadamard":
+        o = kernels.FermionicPQCKernelOracle(n_qubits=n, rotations=rot, entangling_mth=ent).fit(x0)
+        np.testing.assert_allclose(fast[0], o.gram(x0, float32_store=False), rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(fast[1], o.gram(x0, x1, float32_store=False), rtol=RTOL, atol=ATOL)
+    # a depth-2 ansatz couples the pairs: no factorisation
+    k2 = FermionicPQCKernel(n_qubits=4, rotations="X,Z").fit(rng.random((5, 8)))
+    assert k2.depth_ == 2 and k2._block_plan() is None
