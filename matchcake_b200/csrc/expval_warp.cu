@@ -107,6 +107,15 @@ __global__ void __launch_bounds__(192) expval_warp_kernel(WarpCircuit wc, const 
   }
   __syncthreads();
 
+  // initial-state bits as a mask (wire k -> bit k), built once; s_k = -(-1)^bit_k
+  unsigned long long bitmask = 0ull;
+  if (init_bits != nullptr) {
+    const unsigned lo = __ballot_sync(0xffffffffu, lane < n && init_bits[lane]);
+    const unsigned hi = __ballot_sync(0xffffffffu, lane + 32 < n && init_bits[lane + 32 < n ? lane + 32 : 0]);
+    bitmask = ((unsigned long long)hi << 32) | lo;
+  }
+  const double sgn_lane = (tg & 1) ? 1.0 : -1.0;  // bit 0: (+s e, -s o) with s = -1
+
   for (long long b = (long long)blockIdx.x * warps + w; b < B; b += (long long)gridDim.x * warps) {
     const double* prow = params + b * wc.n_param_cols;
     // X = I (lane owns column(s) lane, lane+32), phys = identity
@@ -141,6 +150,15 @@ __global__ void __launch_bounds__(192) expval_warp_kernel(WarpCircuit wc, const 
           // no data moves: cyclic shift of the logical->physical row table over [r0, r0 + s)
           //   forward block: new[0:2] = old[s-2:s], new[i] = old[i-2];   transposed block: new[i] = old[i+2 mod s]
           const int s = 2 * (wc_wire1(code) - wc_wire0(code) + 1);
+          if (s == 4) {  // adjacent wires: rows (0,1) <-> (2,3)
+            unsigned char v = 0;
+            if (lane < 4) v = phys[r0 + (lane ^ 2)];
+            __syncwarp();
+            if (lane < 4) phys[r0 + lane] = v;
+            __syncwarp();
+            ++q;
+            continue;
+          }
           const bool fwd = !((code >> 19) & 1);
           unsigned char v0 = 0, v1 = 0;
           const int i0 = lane, i1 = lane + 32;
@@ -212,20 +230,15 @@ __global__ void __launch_bounds__(192) expval_warp_kernel(WarpCircuit wc, const 
     for (int t = 0; t < T::NT; ++t) c[t][0] = c[t][1] = 0.0;
     for (int g4 = 0; g4 < d; g4 += 4) {
       const int ra = g4 + tg, rb = g4 + (tg ^ 1);
-      const int wire = ra >> 1;
-      double sgn = 0.0;
-      int pa = 0, pb = 0;
-      if (ra < d) {
-        const bool bit = init_bits != nullptr && init_bits[wire];
-        sgn = (bit ? 1.0 : -1.0) * ((tg & 1) ? -1.0 : 1.0);
-        pa = phys[ra];
-        pb = phys[rb];
-      }
+      const bool live = ra < d;
+      const double sgn = ((bitmask >> (ra >> 1)) & 1ull) ? -sgn_lane : sgn_lane;
+      const double* xa = X + (live ? phys[ra] : 0) * LDX + gr;
+      const double* xb = X + (live ? phys[rb] : 0) * LDX + gr;
       double af[MT], bf[MT];
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
-        af[t] = (ra < d) ? sgn * X[pa * LDX + 8 * t + gr] : 0.0;
-        bf[t] = (ra < d) ? X[pb * LDX + 8 * t + gr] : 0.0;
+        af[t] = live ? sgn * xa[8 * t] : 0.0;
+        bf[t] = live ? xb[8 * t] : 0.0;
       }
 #pragma unroll
       for (int ti = 0; ti < MT; ++ti)

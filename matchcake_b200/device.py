@@ -27,6 +27,7 @@ from .operations import (BasisState, CompRotation, CompZX, MatchgateOperation, O
 from .utils.jordan_wigner import JordanWigner, extend_majorana_indices
 
 _UNSET = object()
+_FAST_OPS = frozenset()  # filled below: op classes that go straight into the program
 
 CONTRACTION_STRATEGIES = {None: "none", "none": "none", "neighbours": "neighbours", "horizontal": "horizontal",
                           "vertical": "vertical", "forward": "forward"}
@@ -137,6 +138,9 @@ class NonInteractingFermionicDevice:
         self.show_progress = kwargs.get("show_progress", False)
         self.apply_metadata: defaultdict = defaultdict()
         self._circuit_cache: "OrderedDict[tuple, _ops.CompiledCircuit]" = OrderedDict()
+        self._group_cache: dict = {}
+        self._plan_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
+        self._program_sig: Optional[tuple] = None
         self._state_prep_op: Optional[ProductState] = None
         self._program: List[Operation] = []
         self._sptm: Optional[torch.Tensor] = None
@@ -169,6 +173,7 @@ class NonInteractingFermionicDevice:
 
     def reset(self) -> None:
         self._program = []
+        self._program_sig = None
         self._sptm = None
         self._compiled = None
         self._batched = False
@@ -228,20 +233,28 @@ class NonInteractingFermionicDevice:
             self._wires = tuple(all_wires)
             self._state_prep_op = ProductState.from_basis_state(np.zeros(self.num_wires, dtype=int), wires=self.wires)
         n_ops = 0
-        groups = 0
-        container: dict = {}
-        used: set = set()
+        new_ops: List[Operation] = []
         for i, op in enumerate(ops):
             n_ops = i + 1
-            if type(op).__name__ == "Identity":
-                continue
-            if self.apply_state_prep(op, index=i):
-                continue
-            op = self.convert_op_to_supported(op)
-            expanded = op.decomposition() if isinstance(op, SptmAngleEmbedding) else [op]
-            for e in expanded:
-                self._program.append(e)
-                # emulate the grouping of the chosen contraction strategy for apply_metadata only
+            cls = type(op)
+            if cls not in _FAST_OPS:  # rotations / fSWAPs need no conversion and are never state preparations
+                if cls.__name__ == "Identity":
+                    continue
+                if self.apply_state_prep(op, index=i):
+                    continue
+                op = self.convert_op_to_supported(op)
+                if isinstance(op, SptmAngleEmbedding):
+                    new_ops.extend(op.decomposition())
+                    continue
+            new_ops.append(op)
+        sig = tuple((type(e), e.wires) for e in new_ops)
+        groups = self._group_cache.get((sig, self.contraction_strategy))
+        if groups is None:
+            # emulate the grouping of the chosen contraction strategy (apply_metadata only; the arithmetic is the same)
+            groups = 0
+            container: dict = {}
+            used: set = set()
+            for e in new_ops:
                 cs = tuple(self._wire_index(w) for w in e.wires)
                 span = make_wires_continuous(cs)
                 if self.contraction_strategy == "none":
@@ -254,8 +267,13 @@ class NonInteractingFermionicDevice:
                 else:
                     container[span] = 1
                     used |= set(span)
-        if container:
-            groups += 1
+            if container:
+                groups += 1
+            if len(self._group_cache) > 64:
+                self._group_cache.clear()
+            self._group_cache[(sig, self.contraction_strategy)] = groups
+        self._program.extend(new_ops)
+        self._program_sig = (self._program_sig or ()) + sig
         self._sptm = None
         self._compiled = None
         prev_ops = self.apply_metadata.get("n_operations", 0) if kwargs.get("_accumulate") else 0
@@ -278,6 +296,10 @@ class NonInteractingFermionicDevice:
             return self._compiled
         n = self.num_wires
         dev = self.torch_device
+        fast = self._compile_cached()
+        if fast is not None:
+            self._compiled = fast
+            return fast
         batch = None
         for op in self._program:
             b = self._op_batch(op)
@@ -359,6 +381,62 @@ class NonInteractingFermionicDevice:
         self._compiled = (segments, B)
         return self._compiled
 
+    def _compile_cached(self):
+        """Streams made only of rotation gates and fSWAPs: the circuit descriptor depends on (op classes, wires, which
+        ops share a parameter object), not on the parameter values, so it is cached and only the parameter tensors
+        are gathered per call."""
+        sig = self._program_sig
+        prog = self._program
+        if sig is None or len(sig) != len(prog) or not prog:
+            return None
+        first: dict = {}
+        pattern = []
+        batch = None
+        for i, op in enumerate(prog):
+            if type(op) not in _FAST_OPS:
+                return None
+            p = getattr(op, "_given_params", None)
+            if p is not None:
+                j = first.setdefault(id(p), i)
+                pattern.append(j)
+                if j == i:
+                    shp = p.shape
+                    if len(shp) == 2:
+                        if batch is not None and shp[0] != batch:
+                            raise ValueError(f"Inconsistent batch sizes in the circuit: {batch} and {shp[0]}")
+                        batch = shp[0]
+            else:
+                pattern.append(-1)
+        key = (sig, tuple(pattern), self._wires)
+        plan = self._plan_cache.get(key)
+        if plan is None:
+            gates, sources, col = [], [], {}
+            for i, op in enumerate(prog):
+                idx = tuple(self._wire_index(w) for w in op.wires)
+                if pattern[i] >= 0:
+                    if pattern[i] not in col:
+                        col[pattern[i]] = 2 * len(sources)
+                        sources.append(pattern[i])
+                    gates.append(_ops.GateSpec(op.GATE_KIND, idx[0], idx[1], col[pattern[i]]))
+                else:
+                    lo, hi = min(idx), max(idx)
+                    gates.append(_ops.GateSpec(_ops.GATE_FSWAP, lo, hi, 0, _ops.FLAG_TRANSPOSE if idx[0] != lo else 0))
+            circ = _ops.CompiledCircuit(self.num_wires, gates, 2 * len(sources), device=self.torch_device)
+            plan = (circ, tuple(sources))
+            self._plan_cache[key] = plan
+            while len(self._plan_cache) > 16:
+                self._plan_cache.popitem(last=False)
+        circ, sources = plan
+        self._batched = batch is not None
+        B = batch or 1
+        cols = []
+        for j in sources:
+            t = _as_f64_tensor(prog[j]._given_params, device=self.torch_device).reshape(-1, 2)
+            cols.append(t.expand(B, 2) if (t.shape[0] == 1 and B > 1) else t)
+        params = (torch.cat(cols, dim=1) if len(cols) > 1 else cols[0]).contiguous() if cols else \
+            torch.zeros((B, 0), dtype=torch.float64, device=self.torch_device)
+        return ([("gates", circ, params)], B)
+
     def _materialize(self) -> torch.Tensor:
         """Global SPTM (B, d, d) on the device: product of the segments in application order."""
         if self._sptm is not None:
@@ -398,6 +476,7 @@ class NonInteractingFermionicDevice:
         if t.shape[-1] != 2 * self.num_wires:
             raise ValueError("global_sptm must be (2N, 2N) or (B, 2N, 2N)")
         self._program = [SingleParticleTransitionMatrixOperation(t, wires=self.wires)]
+        self._program_sig = None
         self._compiled = None
         self._batched = t.ndim == 3
         self._sptm = t if t.ndim == 3 else t[None]
@@ -590,5 +669,10 @@ class NonInteractingFermionicDevice:
             raise NotImplementedError(f"Output type {output_type} (sampling) is outside the B200 hot path.")
         raise ValueError(f"Output type {output_type} is not supported.")
 
+
+from .operations import (CompRxRx as _CRx, CompRyRy as _CRy, CompRzRz as _CRz, SptmCompRxRx as _SRx,  # noqa: E402
+                         SptmCompRyRy as _SRy, SptmCompRzRz as _SRz)
+
+_FAST_OPS = frozenset({_CRx, _CRy, _CRz, _SRx, _SRy, _SRz, CompZX, SptmCompZX})
 
 NIFDevice = NonInteractingFermionicDevice
