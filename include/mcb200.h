@@ -89,7 +89,18 @@ int mcb200_circuit_columns(const mcb200_circuit_t* circuit_host, const double* p
 int mcb200_sptm_matmul(const double* A, int64_t strideA, int transA, const double* Bm, int64_t strideB,
                        int transB, double* C, int64_t strideC, int32_t n, int64_t batch, void* stream);
 
+/* Generic matchgate -> SPTM block: U (B, 4, 4) complex as interleaved (re, im) doubles -> blocks_out (B, 4, 4)
+ * real, R_{mu nu} = 1/4 Tr(U c_mu U^dag c_nu) (utils/__init__.py:561-596).  max_imag_out (device double) receives
+ * max |Im R| so that the caller can enforce REAL_PART_ATOL (single_particle_transition_matrix.py:87-113). */
+int mcb200_matchgate_sptm(const double* U_re_im, int64_t B, double* blocks_out, double* max_imag_out, void* stream);
+
 /* ------------------------------------------------------------------ K2: covariance conjugation + gather */
+/* Majorana covariance of product states: amplitudes (B, n, 2) complex as interleaved (re, im) -> cov_out
+ * (B, D, D), D = 2n, or D = 2n + 1 with the displacement column/row when extended != 0
+ * (operations/state_preparation/product_state.py:141-245, _extended_covariance.py:12-98). */
+int mcb200_product_state_cov(const double* amplitudes_re_im, int64_t B, int32_t n_qubits, int32_t extended,
+                             double* cov_out, void* stream);
+
 /* Basis-state input |x>: cov[b] = (R_b^T Lambda_0 R_b)[maj, maj] from X[b] = R_b[:, maj] (d x m);
  * Lambda_0 = (+)_k (-z_k) [[0,1],[-1,0]], z_k = (-1)^{bits[k]} (bits = NULL -> |0..0>).
  * Replaces NonInteractingFermionicDevice.covariance_matrix (nif_device.py:1118-1131) +

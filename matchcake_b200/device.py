@@ -503,7 +503,7 @@ class NonInteractingFermionicDevice:
             x = self._columns(maj)
             bits = torch.as_tensor(sp.basis_state_bits().astype(np.int8), device=self.torch_device)
             return _ops.cov_basis(x, n, bits)
-        l0 = torch.as_tensor(sp.covariance_matrix, device=self.torch_device)
+        l0 = _ops.product_state_cov(torch.as_tensor(sp.data[0], device=self.torch_device))
         idx = None if maj is None else torch.as_tensor(np.asarray(maj, dtype=np.int32), device=self.torch_device)
         return _ops.cov_dense(self._materialize(), l0, idx)
 
@@ -516,7 +516,7 @@ class NonInteractingFermionicDevice:
         return self._out(c if batched else c[0])
 
     def _ext_cov_device(self) -> torch.Tensor:
-        ext0 = torch.as_tensor(self._state_prep_op.extended_covariance_matrix, device=self.torch_device)
+        ext0 = _ops.product_state_cov(torch.as_tensor(self._state_prep_op.data[0], device=self.torch_device), extended=True)
         return _ops.cov_dense(self._materialize(), ext0)
 
     @property

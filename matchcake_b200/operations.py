@@ -128,11 +128,10 @@ class MatchgateOperation(Operation):
         return None if self._matrix.ndim == 2 else self._matrix.shape[0]
 
     @property
-    def single_particle_transition_matrix(self) -> np.ndarray:
-        r"""``R_{\mu\nu} = 1/4 Tr(U c_\mu U^\dagger c_\nu)`` (utils/__init__.py:561-596), evaluated in closed form
-        from the eight non-zero entries: with ``A = [[a,b],[c,d]]`` on the even-parity sector and
-        ``W = [[w,x],[y,z]]`` on the odd one the 4x4 SPTM is real and bilinear in (A, conj W)."""
-        return matchgate_to_sptm_block(self._matrix)
+    def single_particle_transition_matrix(self):
+        r"""``R_{\mu\nu} = 1/4 Tr(U c_\mu U^\dagger c_\nu)`` (utils/__init__.py:561-596), real (…, 4, 4).  Computed by the
+        CUDA library (``mcb200_matchgate_sptm``); raises ``ValueError`` if the imaginary part exceeds 1e-6."""
+        return _ops.matchgate_sptm(torch.as_tensor(self._matrix).to("cuda"))
 
     def to_sptm_operation(self) -> "SingleParticleTransitionMatrixOperation":
         return SingleParticleTransitionMatrixOperation(self.single_particle_transition_matrix, wires=self.wires)

@@ -172,6 +172,38 @@ def sptm_matmul(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b
     return out if (a.ndim == 3 or b.ndim == 3) else out[0]
 
 
+def matchgate_sptm(u: torch.Tensor, atol: float = 1e-6) -> torch.Tensor:
+    """(B, 4, 4) complex matchgates -> (B, 4, 4) real SPTM blocks; raises if the imaginary part exceeds ``atol``."""
+    if not u.is_cuda:
+        raise Mcb200Error("u must live on a CUDA device: matchcake_b200 has no CPU path")
+    u = u.to(torch.complex128).contiguous()
+    single = u.ndim == 2
+    ur = torch.view_as_real(u.reshape(-1, 4, 4)).contiguous()
+    B = ur.shape[0]
+    out = torch.empty((B, 4, 4), dtype=torch.float64, device=u.device)
+    worst = torch.zeros((1,), dtype=torch.float64, device=u.device)
+    check(_lib.load().mcb200_matchgate_sptm(_ptr(ur), B, _ptr(out), _ptr(worst), _stream()))
+    w = float(worst.item())
+    if w > atol:
+        raise ValueError(f"The single-particle transition matrix must be real, but its maximum absolute imaginary "
+                         f"part is {w}, which exceeds {atol}.")
+    return out[0] if single else out
+
+
+def product_state_cov(amplitudes: torch.Tensor, extended: bool = False) -> torch.Tensor:
+    """Per-qubit amplitudes (n, 2) / (B, n, 2) complex -> Majorana covariance (…, D, D), D = 2n (+1 if extended)."""
+    if not amplitudes.is_cuda:
+        raise Mcb200Error("amplitudes must live on a CUDA device: matchcake_b200 has no CPU path")
+    a = amplitudes.to(torch.complex128).contiguous()
+    single = a.ndim == 2
+    ar = torch.view_as_real(a.reshape((-1,) + a.shape[-2:])).contiguous()
+    B, n = ar.shape[0], ar.shape[1]
+    D = 2 * n + (1 if extended else 0)
+    out = torch.empty((B, D, D), dtype=torch.float64, device=a.device)
+    check(_lib.load().mcb200_product_state_cov(_ptr(ar), B, n, int(extended), _ptr(out), _stream()))
+    return out[0] if single else out
+
+
 # ------------------------------------------------------------------------------------------------ covariance
 def cov_basis(x: torch.Tensor, n_qubits: int, bits: Optional[torch.Tensor] = None) -> torch.Tensor:
     """cov[b] = X_b^T Lambda_0(bits) X_b for X (B, d, m)."""

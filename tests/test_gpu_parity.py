@@ -347,3 +347,63 @@ def test_errors_are_loud():
     with pytest.raises(Mcb200Error):
         mops.probs(torch.zeros((1, 140, 140), dtype=torch.float64, device="cuda"),
                    torch.zeros((1, 70), dtype=torch.int8, device="cuda"))
+
+
+def test_matchgate_sptm_kernel():
+    """Generic matchgate -> SPTM on the GPU == trace formula of the reference (utils/__init__.py:561-596)."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(2)
+    us = []
+    for kind in ("XX", "YY", "ZZ"):
+        us.append(gates.matchgate_comp_rotation(rng.uniform(0, 6, (6, 2)), kind))
+    u = np.concatenate(us + [gates.matchgate_fswap()[None]], axis=0)
+    u = np.einsum("bij,bjk->bik", u, u[::-1])  # products of matchgates on the same wires are matchgates
+    ref = gates.enforce_real(gates.sptm_from_gate(u))
+    out = mops.matchgate_sptm(torch.as_tensor(u).cuda()).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+    one = mops.matchgate_sptm(torch.as_tensor(u[3]).cuda()).cpu().numpy()
+    np.testing.assert_allclose(one, ref[3], rtol=RTOL, atol=ATOL)
+    # Tr(U c_mu U^dag c_nu) is a trace of two Hermitian matrices, hence real for ANY U: the REAL_PART_ATOL guard of
+    # the reference can only fire on NaNs here, and the kernel reports max |Im| = rounding noise
+    generic = np.linalg.qr(rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4)))[0]
+    assert np.isfinite(mops.matchgate_sptm(torch.as_tensor(generic).cuda()).cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("n,batch", [(1, None), (3, None), (7, 4), (40, 3)])
+def test_product_state_covariance_kernel(n, batch):
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(n)
+    shape = (n, 2) if batch is None else (batch, n, 2)
+    amp = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    amp /= np.linalg.norm(amp, axis=-1, keepdims=True)
+    cov = mops.product_state_cov(torch.as_tensor(amp).cuda()).cpu().numpy()
+    np.testing.assert_allclose(cov, cv.covariance_matrix(amp), rtol=RTOL, atol=ATOL)
+    ext = mops.product_state_cov(torch.as_tensor(amp).cuda(), extended=True).cpu().numpy()
+    ref = cv.extended_covariance_matrix(cv.covariance_matrix(amp), cv.displacement_vector(amp))
+    np.testing.assert_allclose(ext, ref, rtol=RTOL, atol=ATOL)
+
+
+def test_pair_blocks_match_dense_covariance():
+    """circuit_pair_blocks == the 4x4 diagonal blocks of the dense covariance, with a non-trivial initial state."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(9)
+    n, B = 8, 6
+    ops = []
+    for w in range(0, n, 2):
+        ops += [Op("SptmCompRyRy", (w, w + 1), params=rng.uniform(0, 6, (B, 2))), Op("SptmFSwap", (w, w + 1)),
+                Op("SptmCompRzRz", (w, w + 1), params=rng.uniform(0, 6, (B, 2)))]
+    bits = rng.integers(0, 2, n)
+    r = gates.chain(ops, n, contraction=None)
+    cov = cv.evolve(cv.covariance_matrix(cv.amplitudes_from_basis_state(bits)), r)
+    circ, params = compiled(ops, n, B)
+    blocks = mops.circuit_pair_blocks(circ, params, torch.arange(0, n, 2), torch.as_tensor(bits)).cpu().numpy()
+    iu = np.triu_indices(4, 1)
+    for c in range(n // 2):
+        np.testing.assert_allclose(blocks[:, c], cov[:, 4 * c:4 * c + 4, 4 * c:4 * c + 4][:, iu[0], iu[1]], rtol=RTOL, atol=ATOL)
+    off = cov.copy()
+    for c in range(n // 2):
+        off[:, 4 * c:4 * c + 4, 4 * c:4 * c + 4] = 0
+    assert np.abs(off).max() < 1e-14  # the covariance really is block diagonal
