@@ -1,5 +1,6 @@
 // K1 (dense chain step) and K2 (dense covariance conjugation): strided-batched FP64 GEMM on the FP64 tensor
-// pipe (mma.sync.m8n8k4.f64 -> DMMA), tiles staged through shared memory.
+// pipe (mma.sync.m8n8k4.f64 -> DMMA), tiles staged through shared memory -- by the TMA engine (cp.async.bulk +
+// mbarrier) for the per-instance SPTM products of up to 32 qubits, by register-prefetched loads for larger shapes.
 //
 //   C[b] (M x N) = op(A[b]) (M x K) @ op(B[b]) (K x N),   row-major, op = identity or transpose
 //
@@ -27,6 +28,7 @@ struct GemmArgs {
   long long sA, sB, sC;  // batch strides (elements), 0 = shared
   int M, N, K;
   int lda, ldb, ldc;
+  long long batch;
 };
 
 template <bool TA, bool TB>
@@ -112,6 +114,145 @@ __global__ void __launch_bounds__(256) bgemm_dmma_kernel(GemmArgs g) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------- TMA-staged chain step
+// One block per circuit instance for n <= 64 (<= 32 qubits): both operands are brought into shared memory by the TMA
+// engine -- one cp.async.bulk per matrix row, landing in rows padded to n + 4 doubles so that the DMMA fragment reads
+// stay conflict free -- and completion is signalled on an mbarrier; the 8 warps then compute the 64 x 64 product out
+// of shared memory with m8n8k4 DMMA tiles.  No thread touches global memory for the operands.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int TMA_N = 64;  // largest SPTM side of the TMA-staged path
+
+// NT = padded matrix side (16, 32 or 64).  A block stages G = 8, 4 or 1 instances at a time; WPI = 8 / G warps share
+// one instance, each owning a 16 x min(32, NT) patch of the product.
+template <int NT, bool TA, bool TB>
+__global__ void __launch_bounds__(256) sptm_matmul_tma_kernel(GemmArgs g) {
+  constexpr int LD = NT + 4;
+  constexpr int G = NT == 64 ? 1 : (NT == 32 ? 4 : 8);
+  constexpr int WPI = 8 / G;
+  constexpr int RB = NT / 16;            // 16-row blocks per instance
+  constexpr int JT = NT >= 32 ? 4 : 2;   // 8-column tiles per warp patch
+  constexpr int SLOT = 2 * NT * LD;      // doubles per instance: A then B
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  double* S = reinterpret_cast<double*>(tma_smem);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(S + G * SLOT);
+  const int n = g.M, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = warp / WPI, wl = warp % WPI, wm = wl % RB, wn = wl / RB;
+  const int gr = lane >> 2, tg = lane & 3;
+  if (tid == 0) mbar_init(bar, 1);
+  // rows/columns beyond n are read by the fragment loads of the last tiles: keep them finite
+  for (int e = tid; e < G * SLOT; e += 256) S[e] = 0.0;
+  __syncthreads();
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zero fill before async-proxy writes
+  uint32_t phase = 0;
+  const double* As = S + slot * SLOT;
+  const double* Bs = As + NT * LD;
+  for (long long b0 = (long long)blockIdx.x * G; b0 < g.batch; b0 += (long long)gridDim.x * G) {
+    const int act = (int)min((long long)G, g.batch - b0);
+    if (warp == 0) {
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)act * 2u * (uint32_t)n * (uint32_t)n * 8u);
+      __syncwarp();
+      for (int idx = lane; idx < act * n; idx += 32) {
+        const int sl = idx / n, r = idx - sl * n;
+        double* dst = S + sl * SLOT + r * LD;
+        tma_load_1d(dst, g.A + (b0 + sl) * g.sA + (long long)r * n, (uint32_t)n * 8u, bar);
+        tma_load_1d(dst + NT * LD, g.B + (b0 + sl) * g.sB + (long long)r * n, (uint32_t)n * 8u, bar);
+      }
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    double acc[2][JT][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < JT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int k0 = 0; k0 < n; k0 += 4) {
+      double af[2], bf[JT];
+      const int kk = k0 + tg;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int m = wm * 16 + i * 8 + gr;
+        af[i] = TA ? As[kk * LD + m] : As[m * LD + kk];
+      }
+#pragma unroll
+      for (int j = 0; j < JT; ++j) {
+        const int c = wn * 32 + j * 8 + gr;
+        bf[j] = TB ? Bs[c * LD + kk] : Bs[kk * LD + c];
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < JT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    if (slot < act) {
+      double* C = g.C + (b0 + slot) * g.sC;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < JT; ++j) {
+          const int r = wm * 16 + i * 8 + gr, c = wn * 32 + j * 8 + tg * 2;
+          if (r < n && c < n) {  // n is even on this path, so c + 1 < n as well
+            *reinterpret_cast<double2*>(C + (long long)r * g.ldc + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+          }
+        }
+    }
+    __syncthreads();  // every warp is done reading the slots before the next stage's TMA writes land
+  }
+}
+
+template <int NT>
+static int launch_sptm_tma_nt(const GemmArgs& g, int transA, int transB, cudaStream_t st) {
+  constexpr int G = NT == 64 ? 1 : (NT == 32 ? 4 : 8);
+  const size_t smem = (size_t)G * 2 * NT * (NT + 4) * sizeof(double) + 16;
+  const long long stages = (g.batch + G - 1) / G;
+  const long long resident = (NT == 16 ? 5LL : 3LL) * kNumSMs;
+  long long blocks = stages < resident ? stages : resident;
+  auto go = [&](auto kernel) -> int {
+    if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(sptm_matmul_tma)"))
+      return rc;
+    kernel<<<(unsigned)blocks, 256, smem, st>>>(g);
+    return check_launch("sptm_matmul_tma_kernel");
+  };
+  if (!transA && !transB) return go(sptm_matmul_tma_kernel<NT, false, false>);
+  if (transA && !transB) return go(sptm_matmul_tma_kernel<NT, true, false>);
+  if (!transA && transB) return go(sptm_matmul_tma_kernel<NT, false, true>);
+  return go(sptm_matmul_tma_kernel<NT, true, true>);
+}
+
+static int launch_sptm_tma(const GemmArgs& g, int transA, int transB, cudaStream_t st) {
+  if (g.M <= 16) return launch_sptm_tma_nt<16>(g, transA, transB, st);
+  if (g.M <= 32) return launch_sptm_tma_nt<32>(g, transA, transB, st);
+  return launch_sptm_tma_nt<64>(g, transA, transB, st);
+}
+
 int launch_bgemm(const GemmArgs& g, int transA, int transB, long long batch, cudaStream_t st) {
   if (batch == 0 || g.M == 0 || g.N == 0) return 0;
   for (long long b0 = 0; b0 < batch; b0 += 65535) {
@@ -155,7 +296,11 @@ extern "C" int mcb200_sptm_matmul(const double* A, int64_t strideA, int transA, 
   if (n < 0 || batch < 0) return set_error("sptm_matmul: negative size");
   if (n == 0 || batch == 0) return 0;
   if (A == nullptr || Bm == nullptr || C == nullptr) return set_error("sptm_matmul: NULL pointer");
-  GemmArgs g{A, Bm, C, strideA, strideB, strideC, n, n, n, n, n, n};
+  GemmArgs g{A, Bm, C, strideA, strideB, strideC, n, n, n, n, n, n, batch};
+  // TMA bulk copies need 16-byte aligned rows: even n, 16-byte aligned operands and batch strides
+  const bool aligned = (n % 2 == 0) && (((uintptr_t)A | (uintptr_t)Bm | (uintptr_t)C) % 16 == 0) && (strideA % 2 == 0) &&
+                       (strideB % 2 == 0) && (strideC % 2 == 0);
+  if (n <= TMA_N && aligned) return launch_sptm_tma(g, transA, transB, as_stream(stream));
   return launch_bgemm(g, transA, transB, batch, as_stream(stream));
 }
 
@@ -181,9 +326,9 @@ extern "C" int mcb200_cov_dense(const double* R, int64_t strideR, const double* 
     if (int rc = check_launch("gather_columns_kernel")) return rc;
   }
   // Y = L0 @ X  (D x D @ D x m)
-  GemmArgs g1{L0, X, Y, strideL0, (long long)D * m, (long long)D * m, D, m, D, D, m, m};
+  GemmArgs g1{L0, X, Y, strideL0, (long long)D * m, (long long)D * m, D, m, D, D, m, m, B};
   if (int rc = launch_bgemm(g1, 0, 0, B, st)) return rc;
   // cov = X^T @ Y  (m x D @ D x m)
-  GemmArgs g2{X, Y, cov_out, (long long)D * m, (long long)D * m, (long long)m * m, m, m, D, m, m, m};
+  GemmArgs g2{X, Y, cov_out, (long long)D * m, (long long)D * m, (long long)m * m, m, m, D, m, m, m, B};
   return launch_bgemm(g2, 1, 0, B, st);
 }

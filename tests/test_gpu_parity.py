@@ -285,7 +285,7 @@ def test_sector_features_random_pauli_sums(n, terms):
     np.testing.assert_allclose(total.cpu().numpy(), ref, rtol=RTOL, atol=1e-12)
 
 
-@pytest.mark.parametrize("n,batch", [(8, 3), (32, 5), (70, 2), (128, 2)])
+@pytest.mark.parametrize("n,batch", [(6, 4), (8, 3), (32, 5), (64, 500), (70, 2), (128, 2)])
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
 def test_sptm_matmul(n, batch, ta, tb):
     from matchcake_b200 import ops as mops
