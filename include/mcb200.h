@@ -154,6 +154,18 @@ int mcb200_sector_features(const double* cov, int64_t B, int32_t D, const int32_
 int mcb200_rowdot(const double* feats, const double* coeffs, int64_t B, int32_t T, int32_t accumulate,
                   double* out, void* stream);
 
+/* Fused Hamiltonian read-out for the small sectors:
+ *   out[b] (+)= sum_t coeffs[t] * Pf(cov[b][S_t, S_t]),  S_t = indices[term_ptr[t] .. term_ptr[t+1])
+ * with index sets of MIXED sizes 0 (-> 1), 2, 4 and 6 in one launch (odd sizes contribute 0); cov (B, D, D).
+ * The caller guarantees every set has size <= 6; larger sectors go through mcb200_sector_features + mcb200_rowdot
+ * with accumulate = 1.  Deterministic summation order.
+ * Replaces the sector loop of MPfaffianExpvalStrategy.__call__ (m_pfaffian_expval_strategy.py:270-306) and its
+ * sector_pfaffian_features / tensordot calls (utils/_pfaffian.py:39-75) for Pauli sums whose Majorana strings are
+ * short (nearest-neighbour XX/YY/ZZ/Z Hamiltonians: sectors 2 and 4). */
+int mcb200_pauli_sum_small(const double* cov, int64_t B, int32_t D, const int32_t* term_ptr,
+                           const int32_t* indices, const double* coeffs, int32_t T, int32_t accumulate,
+                           double* out, void* stream);
+
 /* ------------------------------------------------------------------ fused projector expval */
 /* out[b] = <y| rho_b |y> on ALL wires for the circuit applied to the basis state |bits>:
  * one kernel, SPTM columns + covariance + Pfaffian stay on chip (config C2 of BASELINE.json).

@@ -53,6 +53,7 @@ SIGNATURES = {
     "mcb200_probs_all": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "mcb200_sector_features": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "mcb200_rowdot": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    "mcb200_pauli_sum_small": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "mcb200_circuit_expval_projector": (c_i32, [C.POINTER(CircuitStruct), c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "mcb200_gram_workspace_bytes": (c_i64, [c_i64, c_i64, c_i32]),
     "mcb200_gram": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i64, c_i64, c_i32, c_f64, c_vp, c_i64, c_vp, c_vp]),

@@ -142,6 +142,61 @@ __global__ void rowdot_kernel(const double* feats, const double* coeffs, long lo
   if (lane_id() == 0) out[row] = accumulate ? out[row] + s : s;
 }
 
+// Fused Hamiltonian read-out: out[b] (+)= sum_t coeffs[t] * Pf(cov[b][S_t, S_t]) over index sets
+// of MIXED sizes 0, 2, 4, 6 in one launch (m_pfaffian_expval_strategy.py:270-306 loops over sectors and calls
+// sector_pfaffian_features + a tensordot per sector).  One block per instance, threads over terms, closed-form
+// Pfaffians, deterministic tree reduction.  Larger sectors go through mcb200_sector_features + mcb200_rowdot.
+__device__ __forceinline__ double pf4(double a01, double a02, double a03, double a12, double a13, double a23) {
+  return fma(a03, a12, fma(-a02, a13, a01 * a23));
+}
+
+__global__ void pauli_sum_small_kernel(const double* __restrict__ cov, long long B, int D,
+                                       const int32_t* __restrict__ term_ptr, const int32_t* __restrict__ indices,
+                                       const double* __restrict__ coeffs, int T, int accumulate, double* out) {
+  __shared__ double partial[8];
+  for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+    const double* a = cov + b * (long long)D * D;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const int o = term_ptr[t], sz = term_ptr[t + 1] - o;
+      const int32_t* ix = indices + o;
+      double pf = 0.0;
+      if (sz == 0) {
+        pf = 1.0;
+      } else if (sz == 2) {
+        pf = a[(long long)ix[0] * D + ix[1]];
+      } else if (sz == 4) {
+        const long long r0 = (long long)ix[0] * D, r1 = (long long)ix[1] * D, r2 = (long long)ix[2] * D;
+        pf = pf4(a[r0 + ix[1]], a[r0 + ix[2]], a[r0 + ix[3]], a[r1 + ix[2]], a[r1 + ix[3]], a[r2 + ix[3]]);
+      } else if (sz == 6) {
+        double u[6][6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = i + 1; j < 6; ++j) u[i][j] = a[(long long)ix[i] * D + ix[j]];
+        // expansion along row 0: Pf = sum_j (-1)^(j+1) a_0j Pf(A without rows/cols 0 and j)
+        pf = u[0][1] * pf4(u[2][3], u[2][4], u[2][5], u[3][4], u[3][5], u[4][5]);
+        pf = fma(-u[0][2], pf4(u[1][3], u[1][4], u[1][5], u[3][4], u[3][5], u[4][5]), pf);
+        pf = fma(u[0][3], pf4(u[1][2], u[1][4], u[1][5], u[2][4], u[2][5], u[4][5]), pf);
+        pf = fma(-u[0][4], pf4(u[1][2], u[1][3], u[1][5], u[2][3], u[2][5], u[3][5]), pf);
+        pf = fma(u[0][5], pf4(u[1][2], u[1][3], u[1][4], u[2][3], u[2][4], u[3][4]), pf);
+      }  // odd sizes: Pfaffian 0 (utils/_pfaffian.py:64-66)
+      s = fma(coeffs[t], pf, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const int warps = blockDim.x >> 5;
+    if (lane_id() == 0) partial[warp_id()] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < warps; ++w) tot += partial[w];
+      out[b] = accumulate ? out[b] + tot : tot;
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void enumerate_outcomes_kernel(int8_t* bits, int k) {
   // states_to_binary (nif_device.py:151-165): outcome index -> bits, MSB first
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -352,6 +407,21 @@ extern "C" int mcb200_rowdot(const double* feats, const double* coeffs, int64_t 
   if (out == nullptr || (T > 0 && (feats == nullptr || coeffs == nullptr))) return set_error("rowdot: NULL pointer");
   rowdot_kernel<<<(unsigned)((B + 7) / 8), 256, 0, as_stream(stream)>>>(feats, coeffs, B, T, accumulate, out);
   return check_launch("rowdot_kernel");
+}
+
+extern "C" int mcb200_pauli_sum_small(const double* cov, int64_t B, int32_t D, const int32_t* term_ptr,
+                                      const int32_t* indices, const double* coeffs, int32_t T, int32_t accumulate,
+                                      double* out, void* stream) {
+  if (B < 0 || T < 0 || D < 1) return set_error("pauli_sum_small: bad sizes");
+  if (B == 0) return 0;
+  if (out == nullptr) return set_error("pauli_sum_small: out is NULL");
+  if (T > 0 && (cov == nullptr || term_ptr == nullptr || coeffs == nullptr))
+    return set_error("pauli_sum_small: NULL pointer");
+  const int threads = T <= 32 ? 32 : T <= 64 ? 64 : T <= 128 ? 128 : 256;
+  const long long cap = 32LL * kNumSMs;
+  pauli_sum_small_kernel<<<(unsigned)(B < cap ? B : cap), threads, 0, as_stream(stream)>>>(
+      cov, B, D, term_ptr, indices, coeffs, T, accumulate, out);
+  return check_launch("pauli_sum_small_kernel");
 }
 
 extern "C" int64_t mcb200_gram_workspace_bytes(int64_t n0, int64_t n1, int32_t d) {

@@ -93,6 +93,7 @@ class NonInteractingFermionicDevice:
     DEFAULT_PROB_STRATEGY = "LookupTable"
     DEFAULT_CONTRACTION_METHOD = "neighbours"
     FUSED_MAX_QUBITS = 59  # shared-memory limit of the fused projector kernel
+    FUSED_SECTOR_MAX = 6   # Majorana strings up to this length take the fused Pauli-sum kernel
 
     @staticmethod
     def states_to_binary(samples: np.ndarray, num_wires: int, dtype: type = np.int64) -> np.ndarray:
@@ -620,7 +621,22 @@ class NonInteractingFermionicDevice:
         ext = self._ext_cov_device()
         total = None
         coeffs_arr = np.asarray(coeffs, dtype=complex)
+        # sectors of size <= 6 (nearest-neighbour Hamiltonians live there): one fused gather + Pfaffian + dot launch
+        small = [s for s in structure if s <= self.FUSED_SECTOR_MAX]
+        if small:
+            sizes, flat, scal = [], [], []
+            for sector in small:
+                index_sets, phases, terms, wick = structure[sector]
+                sizes.extend([sector] * len(terms))
+                flat.append(index_sets.reshape(-1))
+                scal.append(np.real(coeffs_arr[terms] * phases * wick))
+            term_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+            flat = np.concatenate(flat).astype(np.int32) if flat else np.zeros(0, np.int32)
+            total = _ops.pauli_sum_small(ext, torch.as_tensor(term_ptr), torch.as_tensor(flat),
+                                         torch.as_tensor(np.concatenate(scal).astype(np.float64)))
         for sector, (index_sets, phases, terms, wick) in structure.items():
+            if sector <= self.FUSED_SECTOR_MAX:
+                continue
             scalar = np.real(coeffs_arr[terms] * phases * wick).astype(np.float64)
             feats = _ops.sector_features(ext, torch.as_tensor(index_sets.reshape(len(terms), sector)))
             total = _ops.rowdot(feats, torch.as_tensor(scalar, device=self.torch_device), out=total)

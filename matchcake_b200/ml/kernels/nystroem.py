@@ -1,20 +1,24 @@
 """``Nystroem`` kernel approximation (mirrors /root/reference/src/matchcake/ml/kernels/nystroem.py:11-136).
 
 The two Gram builds (landmark square Gram in ``fit``, rectangular ``K(X, landmarks)`` in ``transform``) run on the
-GPU through the kernel; the SVD of the landmark Gram and the final projection are the reference's numpy/scipy
-tail (not part of the metric)."""
+GPU through the kernel.  The tail (SVD of the landmark Gram, ``embedded @ normalization_.T``;
+not part of the metric) stays on the device as well when the kernel hands back CUDA tensors -- plain library calls
+(cuSOLVER ``gesvd`` / cuBLAS DGEMM through torch) in float64, so an ``(n, 4096)`` embedding never crosses PCIe twice.
+``U diag(S^-1/2) V`` does not depend on the sign / basis choices of the SVD, so the result matches scipy's to rounding."""
 from __future__ import annotations
 
 import numpy as np
 import torch
-from scipy.linalg import svd
 from sklearn.kernel_approximation import Nystroem as sk_Nystroem
 from sklearn.utils import check_random_state
 from sklearn.utils.validation import check_is_fitted
 
 
-def _to_numpy(x):
-    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+def _to_device(x):
+    """float64 tensor; stays where the kernel left it (CUDA for the kernels of this package)."""
+    if isinstance(x, torch.Tensor):
+        return x.detach().to(torch.float64)
+    return torch.as_tensor(np.asarray(x), dtype=torch.float64)
 
 
 class Nystroem(sk_Nystroem):
@@ -29,10 +33,11 @@ class Nystroem(sk_Nystroem):
         inds = rnd.permutation(n_samples)
         basis_inds = inds[:n_components]
         basis = X[basis_inds]
-        basis_kernel = _to_numpy(self.kernel(basis))
-        U, S, V = svd(basis_kernel)
-        S = np.maximum(S, 1e-12)
-        self.normalization_ = np.dot(U / np.sqrt(S), V)
+        basis_kernel = _to_device(self.kernel(basis))
+        U, S, V = torch.linalg.svd(basis_kernel)                      # nystroem.py:96
+        S = torch.clamp(S, min=1e-12)                                 # nystroem.py:97
+        self._normalization_dev = (U / torch.sqrt(S)) @ V             # nystroem.py:98
+        self.normalization_ = self._normalization_dev.cpu().numpy()
         self.components_ = basis
         self.component_indices_ = basis_inds
         self._n_features_out = n_components
@@ -40,8 +45,11 @@ class Nystroem(sk_Nystroem):
 
     def transform(self, X):
         check_is_fitted(self)
-        embedded = _to_numpy(self.kernel(X, self.components_))
-        return np.dot(embedded, self.normalization_.T)
+        embedded = _to_device(self.kernel(X, self.components_))
+        norm = getattr(self, "_normalization_dev", None)
+        if norm is None or norm.device != embedded.device:            # e.g. after unpickling / sklearn.clone
+            norm = self._normalization_dev = torch.as_tensor(self.normalization_, dtype=torch.float64, device=embedded.device)
+        return (embedded @ norm.T).cpu().numpy()                      # nystroem.py:123
 
     def freeze(self):
         self.kernel.freeze()

@@ -309,6 +309,25 @@ def rowdot(feats: torch.Tensor, coeffs: torch.Tensor, out: Optional[torch.Tensor
     return out
 
 
+def pauli_sum_small(cov: torch.Tensor, term_ptr: torch.Tensor, indices: torch.Tensor, coeffs: torch.Tensor,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b] (+)= sum_t coeffs[t] Pf(cov[b][S_t, S_t]) for index sets of mixed sizes <= 6 (one launch)."""
+    cov = _f64(cov, "cov")
+    B, D = cov.shape[0], cov.shape[-1]
+    term_ptr = term_ptr.to(device=cov.device, dtype=torch.int32).contiguous()
+    indices = indices.to(device=cov.device, dtype=torch.int32).contiguous()
+    coeffs = _f64(coeffs.to(cov.device), "coeffs")
+    T = coeffs.shape[0]
+    if term_ptr.shape[0] != T + 1:
+        raise Mcb200Error(f"pauli_sum_small: term_ptr must have {T + 1} entries, got {term_ptr.shape[0]}")
+    acc = out is not None
+    if out is None:
+        out = torch.empty((B,), dtype=torch.float64, device=cov.device)
+    check(_lib.load().mcb200_pauli_sum_small(_ptr(cov), B, D, _ptr(term_ptr), _ptr(indices), _ptr(coeffs), T, int(acc),
+                                             _ptr(out), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ Gram
 def gram(cov0: torch.Tensor, cov1: torch.Tensor, scale: float, mode: int = GRAM_REFERENCE,
          row_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:

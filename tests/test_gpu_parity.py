@@ -285,6 +285,50 @@ def test_sector_features_random_pauli_sums(n, terms):
     np.testing.assert_allclose(total.cpu().numpy(), ref, rtol=RTOL, atol=1e-12)
 
 
+@pytest.mark.parametrize("n,terms,B", [(5, 40, 4), (9, 200, 3), (4, 300, 70)])
+def test_pauli_sum_small_fused_matches_oracle(n, terms, B):
+    """Mixed-size sectors (0, 2, 4, 6) in ONE launch; longer Majorana strings accumulate through the sector path."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(100 + n)
+    r = gates.random_sptm(n, seed=n, batch_size=B)
+    amp = rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))
+    amp /= np.linalg.norm(amp, axis=1, keepdims=True)
+    # mostly short strings (nearest-neighbour style) plus a few arbitrary ones
+    words = []
+    for t in range(terms):
+        w = ["I"] * n
+        if t % 5 == 4:
+            w = list(rng.choice(list("IXYZ"), n))
+        else:
+            q = int(rng.integers(0, n - 1))
+            w[q] = str(rng.choice(list("XYZ")))
+            if t % 2:
+                w[q + 1] = str(rng.choice(list("XYZ")))
+        words.append("".join(w))
+    words[0] = "I" * n
+    coeffs = rng.standard_normal(terms)
+    ref = readout.expval_pauli_sum(cv.evolved_extended_covariance(amp, r), words, coeffs)
+    ext0 = cv.extended_covariance_matrix(cv.covariance_matrix(amp), cv.displacement_vector(amp))
+    ext = mops.cov_dense(dev(r), dev(ext0))
+    structure = readout.pauli_sum_structure(words, coeffs, n)
+    sizes, flat, scal = [], [], []
+    for sector, (idx, sc) in structure.items():
+        if sector <= 6:
+            sizes += [sector] * len(sc)
+            flat.append(np.asarray(idx, dtype=np.int32).reshape(-1))
+            scal.append(sc)
+    assert {0, 2, 4} <= set(sizes)
+    term_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    total = mops.pauli_sum_small(ext, torch.as_tensor(term_ptr), torch.as_tensor(np.concatenate(flat)),
+                                 torch.as_tensor(np.concatenate(scal)))
+    for sector, (idx, sc) in structure.items():
+        if sector > 6:
+            feats = mops.sector_features(ext, torch.as_tensor(idx.reshape(len(sc), sector), dtype=torch.int32))
+            total = mops.rowdot(feats, dev(sc), out=total)
+    np.testing.assert_allclose(total.cpu().numpy(), ref, rtol=RTOL, atol=1e-12)
+
+
 @pytest.mark.parametrize("n,batch", [(6, 4), (8, 3), (32, 5), (64, 500), (70, 2), (128, 2)])
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
 def test_sptm_matmul(n, batch, ta, tb):
