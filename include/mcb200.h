@@ -217,6 +217,39 @@ void mcb200_reset_launch_count(void);
  * (kind 0) or a DMMA m8n8k4 loop (kind 1) and returns achieved TFLOP/s (< 0 on error). */
 double mcb200_probe_fp64_tflops(int32_t kind, int32_t iters, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Reverse-mode derivatives.  The reference differentiates this path with torch autograd
+ * (devices/nif_device.py:949-989 advertises backprop; ml/kernels/kernel.py:200-283 trains through the Gram; the
+ * Pfaffian derivative d Pf = Pf/2 tr(A^-1 dA) is torch_pfaffian's, pinned by tests/test_utils/test_pfaffian.py:86-115).
+ * Each call is the adjoint of the forward entry point of the same name; grad_* outputs are OVERWRITTEN.
+ * Matrix sizes up to 128; a singular matrix (forward value exactly 0) contributes a zero gradient.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* grad_A[n] = grad_out[n] * out[n] / 2 * A[n]^-T   (out = the forward result of mcb200_pfaffian, either mode). */
+int mcb200_pfaffian_backward(const double* A, int64_t n, int32_t m, const double* out, const double* grad_out,
+                             double* grad_A, void* stream);
+
+/* Adjoint of mcb200_probs with normalize = 0: grad_cov[b] = sum_q grad_p[b,q] p[b,q] / 2 (cov[b] + Lambda_y(q))^-T. */
+int mcb200_probs_backward(const double* cov, const int8_t* outcomes, int64_t B, int32_t Q, int32_t k,
+                          const double* p, const double* grad_p, double* grad_cov, void* stream);
+
+/* Adjoint of mcb200_sector_features: scatters grad_feats[b,t] feats[b,t] / 2 (sub-block)^-T into grad_cov (B, D, D). */
+int mcb200_sector_features_backward(const double* cov, int64_t B, int32_t D, const int32_t* index_sets, int32_t T,
+                                    int32_t s, const double* feats, const double* grad_feats, double* grad_cov,
+                                    void* stream);
+
+/* Adjoint of mcb200_cov_basis: grad_X = Lambda_0 X (grad_cov^T - grad_cov), X and grad_X (B, 2N, m). */
+int mcb200_cov_basis_backward(const double* X, const int8_t* bits, int64_t B, int32_t n_qubits, int32_t m,
+                              const double* grad_cov, double* grad_X, void* stream);
+
+/* Adjoint of mcb200_circuit_columns.  X is the forward OUTPUT (B, 2N, m); the gates are un-applied in application
+ * order, nothing has to be saved by the forward pass.  grad_angles (B, n_param_cols) is the derivative with respect
+ * to the angle each gate actually used, i.e. AFTER the optional affine map bias + scale * x of the descriptor
+ * (the caller finishes the chain rule for x / bias / scale); explicit 4x4 parameter blocks receive the derivative
+ * of their 16 entries. */
+int mcb200_circuit_columns_backward(const mcb200_circuit_t* circuit, const double* params, int64_t B, int32_t m,
+                                    const double* X, const double* grad_X, double* grad_angles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

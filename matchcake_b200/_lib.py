@@ -60,6 +60,11 @@ SIGNATURES = {
     "mcb200_circuit_pair_blocks": (c_i32, [C.POINTER(CircuitStruct), c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "mcb200_gram_blocks4": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i64, c_i64, c_i32, c_f64, c_vp, c_i64, c_vp]),
     "mcb200_gram_symmetrize": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp]),
+    "mcb200_pfaffian_backward": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "mcb200_probs_backward": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "mcb200_sector_features_backward": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "mcb200_cov_basis_backward": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "mcb200_circuit_columns_backward": (c_i32, [C.POINTER(CircuitStruct), c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "mcb200_launch_count": (c_i64, []),
     "mcb200_reset_launch_count": (None, []),
     "mcb200_probe_fp64_tflops": (c_f64, [c_i32, c_i32, c_vp]),

@@ -24,7 +24,7 @@ struct PlainLoader {
     const double* src = A + item * (long long)m * m;
     for (int idx = tid; idx < m * m; idx += nthr) {
       int i = idx / m, j = idx - i * m;
-      if (i < j) S[i * lds + j] = src[idx];
+      if (i < j) S[i * lds + j] = 0.5 * (src[idx] - src[j * m + i]);  // skew part, see pfaffian_src.cuh
     }
   }
   __device__ void store(long long item, double pf) const {

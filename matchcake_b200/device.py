@@ -322,7 +322,7 @@ class NonInteractingFermionicDevice:
             key = id(p)
             if key in col_of:
                 return col_of[key]
-            t = _as_f64_tensor(p, device=dev).reshape(-1, width)
+            t = _as_f64_tensor(p, device=dev, keep_grad=True).reshape(-1, width)
             if t.shape[0] == 1 and B > 1:
                 t = t.expand(B, width)
             cols.append(t)
@@ -368,7 +368,7 @@ class NonInteractingFermionicDevice:
                         gates.append(_ops.GateSpec(_ops.GATE_BLOCK4_PARAM, idx[0], idx[1], param_offset(m, 16)))
                 else:
                     flush()
-                    mt = _as_f64_tensor(m, device=dev)
+                    mt = _as_f64_tensor(m, device=dev, keep_grad=True)
                     d = 2 * n
                     if mt.shape[-1] != d:
                         full = torch.eye(d, dtype=torch.float64, device=dev)
@@ -432,7 +432,7 @@ class NonInteractingFermionicDevice:
         B = batch or 1
         cols = []
         for j in sources:
-            t = _as_f64_tensor(prog[j]._given_params, device=self.torch_device).reshape(-1, 2)
+            t = _as_f64_tensor(prog[j]._given_params, device=self.torch_device, keep_grad=True).reshape(-1, 2)
             cols.append(t.expand(B, 2) if (t.shape[0] == 1 and B > 1) else t)
         params = (torch.cat(cols, dim=1) if len(cols) > 1 else cols[0]).contiguous() if cols else \
             torch.zeros((B, 0), dtype=torch.float64, device=self.torch_device)
@@ -516,7 +516,18 @@ class NonInteractingFermionicDevice:
         batched = self._batched or self._state_prep_op.batch_size is not None
         return self._out(c if batched else c[0])
 
+    def _grad_mode(self) -> bool:
+        """True when a circuit parameter requires grad: read-outs then take the differentiable (unfused) kernels."""
+        if not torch.is_grad_enabled():
+            return False
+        segments, _ = self._compile()
+        return any(isinstance(t, torch.Tensor) and t.requires_grad for seg in segments for t in seg[1:])
+
     def _ext_cov_device(self) -> torch.Tensor:
+        if self._grad_mode() and self._is_basis_input():
+            # basis states have no displacement: the extended covariance is the covariance bordered by zeros, and
+            # cov_basis has an adjoint kernel (cov_dense does not)
+            return torch.nn.functional.pad(self._cov_device(), (0, 1, 0, 1))
         ext0 = _ops.product_state_cov(torch.as_tensor(self._state_prep_op.data[0], device=self.torch_device), extended=True)
         return _ops.cov_dense(self._materialize(), ext0)
 
@@ -622,7 +633,8 @@ class NonInteractingFermionicDevice:
         total = None
         coeffs_arr = np.asarray(coeffs, dtype=complex)
         # sectors of size <= 6 (nearest-neighbour Hamiltonians live there): one fused gather + Pfaffian + dot launch
-        small = [s for s in structure if s <= self.FUSED_SECTOR_MAX]
+        fused_max = -1 if ext.requires_grad else self.FUSED_SECTOR_MAX  # the fused read-out is inference-only
+        small = [s for s in structure if s <= fused_max]
         if small:
             sizes, flat, scal = [], [], []
             for sector in small:
@@ -635,7 +647,7 @@ class NonInteractingFermionicDevice:
             total = _ops.pauli_sum_small(ext, torch.as_tensor(term_ptr), torch.as_tensor(flat),
                                          torch.as_tensor(np.concatenate(scal).astype(np.float64)))
         for sector, (index_sets, phases, terms, wick) in structure.items():
-            if sector <= self.FUSED_SECTOR_MAX:
+            if sector <= fused_max:
                 continue
             scalar = np.real(coeffs_arr[terms] * phases * wick).astype(np.float64)
             feats = _ops.sector_features(ext, torch.as_tensor(index_sets.reshape(len(terms), sector)))

@@ -36,26 +36,35 @@ class FermionicPQCKernel(NIFKernel):
 
     def __init__(self, *, gram_batch_size: int = NIFKernel.DEFAULT_GRAM_BATCH_SIZE,
                  random_state: int = NIFKernel.DEFAULT_RANDOM_STATE, alignment: bool = NIFKernel.DEFAULT_ALIGNMENT,
+                 alignment_iterations: int = NIFKernel.DEFAULT_ALIGNMENT_ITERATIONS,
+                 alignment_learning_rate: float = NIFKernel.DEFAULT_ALIGNMENT_LEARNING_RATE,
+                 alignment_early_stopping_patience: int = NIFKernel.DEFAULT_ALIGNMENT_EARLY_STOPPING_PATIENCE,
+                 alignment_early_stopping_threshold: float = NIFKernel.DEFAULT_ALIGNMENT_EARLY_STOPPING_THRESHOLD,
                  n_qubits: int = NIFKernel.DEFAULT_N_QUBITS, r_dtype: Optional[torch.dtype] = None,
                  c_dtype: Optional[torch.dtype] = None, rotations: str = DEFAULT_ROTATIONS,
                  entangling_mth: str = DEFAULT_ENTANGLING_MTH):
         super().__init__(gram_batch_size=gram_batch_size, random_state=random_state, alignment=alignment,
+                         alignment_iterations=alignment_iterations, alignment_learning_rate=alignment_learning_rate,
+                         alignment_early_stopping_patience=alignment_early_stopping_patience,
+                         alignment_early_stopping_threshold=alignment_early_stopping_threshold,
                          n_qubits=n_qubits, r_dtype=r_dtype, c_dtype=c_dtype)
         self.rotations = rotations
         self.entangling_mth = entangling_mth
         if self.entangling_mth not in self.available_entangling_mth:
             raise ValueError(f"Unknown entangling method: {self.entangling_mth}.")
         self.depth_: Optional[int] = None
-        self.bias_: Optional[np.ndarray] = None
-        self.data_scaling_: Optional[np.ndarray] = None
+        self.register_parameter("bias_", None)                # trainable (kernel alignment), float64 on the GPU
+        self.data_scaling_: Optional[torch.Tensor] = None
         self._circuit = None
+        self._circuit_key = None
         self._plan = None
 
     def fit(self, x_train, y_train=None):
         x_arr = x_train.detach().cpu().numpy() if isinstance(x_train, torch.Tensor) else np.asarray(x_train)
         n_inputs = int(np.prod(x_arr.shape[1:]))
-        self.bias_ = self.np_rn_gen.random(n_inputs)
-        self.data_scaling_ = np.pi * np.ones(n_inputs)
+        # fermionic_pqc_kernel.py:155-160: bias_ is the kernel's only registered parameter
+        self.bias_ = torch.nn.Parameter(torch.from_numpy(self.np_rn_gen.random(n_inputs)).to("cuda"))
+        self.data_scaling_ = torch.pi * torch.ones(n_inputs, dtype=torch.float64, device="cuda")
         if self.depth_ is None:
             self.depth_ = int(max(1, np.ceil(x_arr.shape[-1] / self.n_qubits)))
         self._circuit = None
@@ -70,7 +79,7 @@ class FermionicPQCKernel(NIFKernel):
         """Yields the same operation stream as the reference (fermionic_pqc_kernel.py:166-199)."""
         xt = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x, dtype=torch.float64)
         xt = xt.reshape(len(xt), -1).cpu()
-        xt = torch.as_tensor(self.bias_) + torch.as_tensor(self.data_scaling_) * xt
+        xt = self.bias_.detach().cpu() + self.data_scaling_.cpu() * xt
         patterns = [pattern_double(self.n_qubits), pattern_double_odd(self.n_qubits)]
         for layer in range(self.depth_):
             sub_x = xt[..., layer * self.n_qubits:(layer + 1) * self.n_qubits]
@@ -87,8 +96,10 @@ class FermionicPQCKernel(NIFKernel):
     def _compiled(self):
         """The ansatz as ONE device circuit; features are the parameter columns and ``bias + pi * x`` is applied
         inside the kernel, so no per-gate Python objects and no elementwise pre-pass exist on the hot path."""
-        if self._circuit is not None:
+        key = (self.bias_._version, self.bias_.data_ptr())  # an optimiser step on bias_ invalidates the baked affine
+        if self._circuit is not None and self._circuit_key == key:
             return self._circuit
+        self._circuit_key = key
         nq, f = self.n_qubits, len(self.bias_)
         gates: List[_ops.GateSpec] = []
         col_index: List[int] = []   # parameter column -> feature column (f = the constant-zero pad column)
@@ -110,14 +121,26 @@ class FermionicPQCKernel(NIFKernel):
                     gates.append(_ops.GateSpec(_ops.GATE_BLOCK4_CONST, w0, w1, len(consts)))
                     consts.extend(_hh_block().reshape(-1).tolist())
         idx = np.asarray(col_index, dtype=np.int64)
-        bias = np.concatenate([self.bias_, [0.0]])[idx]
-        scale = np.concatenate([self.data_scaling_, [0.0]])[idx]
+        bias = np.concatenate([self.bias_.detach().cpu().numpy(), [0.0]])[idx]
+        scale = np.concatenate([self.data_scaling_.cpu().numpy(), [0.0]])[idx]
         identity = len(idx) == f and np.array_equal(idx, np.arange(f))
         circ = _ops.CompiledCircuit(nq, gates, len(idx), scale=scale, bias=bias,
                                     consts=np.asarray(consts) if consts else None)
         self._compiled_host = (gates, scale, bias, consts)
         self._circuit = (circ, None if identity else torch.as_tensor(idx, device="cuda"))
+        self._circuit_plain = None
+        self._gates_host = (gates, consts)
         return self._circuit
+
+    def _compiled_plain(self) -> _ops.CompiledCircuit:
+        """Same gate list WITHOUT the in-kernel affine map: under autograd ``bias_ + scale * x`` is a torch expression
+        so that the chain rule reaches ``bias_`` (the adjoint kernel returns d/d angle)."""
+        circ, _ = self._compiled()
+        if self._circuit_plain is None:
+            gates, consts = self._gates_host
+            self._circuit_plain = _ops.CompiledCircuit(self.n_qubits, gates, circ.n_param_cols,
+                                                       consts=np.asarray(consts) if consts else None)
+        return self._circuit_plain
 
     def _features(self, x) -> torch.Tensor:
         xt = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x))
@@ -129,6 +152,15 @@ class FermionicPQCKernel(NIFKernel):
         return xt.contiguous()
 
     def _x_to_sptm(self, x) -> torch.Tensor:
+        if self._differentiating():
+            xt = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x))
+            xt = xt.to(device="cuda", dtype=torch.float64).reshape(len(xt), -1)
+            angles = self.bias_ + self.data_scaling_ * xt                  # fermionic_pqc_kernel.py:181
+            _, gather = self._compiled()
+            if gather is not None:
+                angles = torch.cat([angles, torch.zeros((len(xt), 1), dtype=torch.float64, device="cuda")], dim=1)
+                angles = angles.index_select(1, gather)
+            return _ops.circuit_columns(self._compiled_plain(), angles.contiguous())
         return _ops.circuit_columns(self._compiled()[0], self._features(x))
 
     # ------------------------------------------------------------------ independent wire pairs (block-diagonal SPTM)

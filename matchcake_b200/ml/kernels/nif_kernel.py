@@ -33,9 +33,16 @@ class NIFKernel(Kernel):
 
     def __init__(self, *, gram_batch_size: int = Kernel.DEFAULT_GRAM_BATCH_SIZE,
                  random_state: int = Kernel.DEFAULT_RANDOM_STATE, alignment: bool = Kernel.DEFAULT_ALIGNMENT,
+                 alignment_iterations: int = Kernel.DEFAULT_ALIGNMENT_ITERATIONS,
+                 alignment_learning_rate: float = Kernel.DEFAULT_ALIGNMENT_LEARNING_RATE,
+                 alignment_early_stopping_patience: int = Kernel.DEFAULT_ALIGNMENT_EARLY_STOPPING_PATIENCE,
+                 alignment_early_stopping_threshold: float = Kernel.DEFAULT_ALIGNMENT_EARLY_STOPPING_THRESHOLD,
                  n_qubits: int = DEFAULT_N_QUBITS, r_dtype: Optional[torch.dtype] = None,
                  c_dtype: Optional[torch.dtype] = None):
-        super().__init__(gram_batch_size=gram_batch_size, random_state=random_state, alignment=alignment)
+        super().__init__(gram_batch_size=gram_batch_size, random_state=random_state, alignment=alignment,
+                         alignment_iterations=alignment_iterations, alignment_learning_rate=alignment_learning_rate,
+                         alignment_early_stopping_patience=alignment_early_stopping_patience,
+                         alignment_early_stopping_threshold=alignment_early_stopping_threshold)
         self._r_dtype = r_dtype or self.DEFAULT_R_DTYPE
         self._c_dtype = c_dtype or self.DEFAULT_C_DTYPE
         self._n_qubits = int(n_qubits)
@@ -115,11 +122,21 @@ class NIFKernel(Kernel):
     def sptms_train(self) -> torch.Tensor:
         return self._x_to_sptm(self.x_train_)
 
+    def _state_key(self):
+        """Identity of the training inputs and the version of every parameter: cached per-sample data is stale once an
+        optimiser step (kernel alignment) has touched a parameter."""
+        return (id(self.x_train_),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
     @property
     def covs_train(self) -> torch.Tensor:
-        if self._covs_train is None or self._covs_train[0] is not self.x_train_:
-            self._covs_train = (self.x_train_, self._x_to_cov(self.x_train_))
+        key = self._state_key()
+        if self._covs_train is None or self._covs_train[0] != key:
+            self._covs_train = (key, self._x_to_cov(self.x_train_))
         return self._covs_train[1]
+
+    def _differentiating(self) -> bool:
+        """Train mode with a parameter that requires grad: take the differentiable route."""
+        return self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def _block_plan(self):
         """Sub-circuits per independent wire pair, or None (subclasses with a compiled ansatz override this)."""
@@ -131,11 +148,18 @@ class NIFKernel(Kernel):
     def compute_similarities(self, x0, x1, **kwargs) -> torch.Tensor:
         same = x1 is x0
         full = kwargs.get("full_rectangle", False)
+        if self._differentiating():
+            # kernel alignment (kernel.py:200-283): K1 -> K2 -> Pfaffian through the ops that have adjoint kernels
+            cov0 = self._x_to_cov(x0)
+            cov1 = cov0 if same else self._x_to_cov(x1)
+            k = _ops.gram(cov0, cov1, 2.0 ** (-self._n_qubits), mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE)
+            return k.to(self.R_DTYPE)
         if self.use_block_factorisation and self._block_plan() is not None:
             b0 = self._x_to_blocks(x0)
             if kwargs.get("x1_train", False):
-                if self._blocks_train is None or self._blocks_train[0] is not self.x_train_:
-                    self._blocks_train = (self.x_train_, self._x_to_blocks(self.x_train_))
+                key = self._state_key()
+                if self._blocks_train is None or self._blocks_train[0] != key:
+                    self._blocks_train = (key, self._x_to_blocks(self.x_train_))
                 b1 = self._blocks_train[1]
             else:
                 b1 = b0 if same else self._x_to_blocks(x1)

@@ -40,9 +40,9 @@ def _shape(x) -> Tuple[int, ...]:
     return tuple(x.shape) if hasattr(x, "shape") else tuple(np.shape(x))
 
 
-def _as_f64_tensor(x, device=None) -> torch.Tensor:
+def _as_f64_tensor(x, device=None, keep_grad: bool = False) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
-        t = x.detach()
+        t = x if (keep_grad and x.requires_grad and torch.is_grad_enabled()) else x.detach()
         if t.is_complex():
             t = t.real
     else:

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import autograd as _ag
 from ._lib import CircuitStruct, Mcb200Error, check
 
 GATE_RXRX, GATE_RYRY, GATE_RZRZ, GATE_FSWAP, GATE_BLOCK4_CONST, GATE_BLOCK4_PARAM = range(6)
@@ -128,6 +129,8 @@ class CompiledCircuit:
 
 def circuit_columns(circ: CompiledCircuit, params: torch.Tensor, cols: Optional[torch.Tensor] = None) -> torch.Tensor:
     """X[b] = R_b[:, cols] (B, d, m); ``cols=None`` gives the full SPTM (B, d, d)."""
+    if _ag.needs_grad(params):
+        return _ag.CircuitColumns.apply(params, circ, cols)
     params = circ._params(params)
     B = params.shape[0]
     if cols is not None:
@@ -144,6 +147,13 @@ def circuit_columns(circ: CompiledCircuit, params: torch.Tensor, cols: Optional[
 def circuit_expval_projector(circ: CompiledCircuit, params: torch.Tensor, init_bits: Optional[torch.Tensor] = None,
                              target_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
     """<y|rho_b|y> on all wires, one fused kernel (B,)."""
+    if _ag.needs_grad(params):  # differentiable route: K1 -> K2 -> K3 as separate ops, each with its adjoint kernel
+        n = circ.n_qubits
+        dev = params.device
+        cov = cov_basis(circuit_columns(circ, params), n, init_bits)
+        tgt = torch.zeros((1, n), dtype=torch.int8, device=dev) if target_bits is None else \
+            target_bits.to(device=dev, dtype=torch.int8).reshape(1, n)
+        return probs(cov, tgt)[:, 0]
     params = circ._params(params)
     B = params.shape[0]
     bits = lambda t: None if t is None else t.to(device=params.device, dtype=torch.int8).contiguous()
@@ -156,6 +166,8 @@ def circuit_expval_projector(circ: CompiledCircuit, params: torch.Tensor, init_b
 
 def sptm_matmul(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False) -> torch.Tensor:
     """Batched dense chain step C = op(a) @ op(b); a/b are (n,n) or (B,n,n) (a 2-D operand is shared)."""
+    if _ag.needs_grad(a, b):
+        return _ag.SptmMatmul.apply(a, b, trans_a, trans_b)
     a, b = _f64(a, "a"), _f64(b, "b")
     n = a.shape[-1]
     if a.shape[-2:] != (n, n) or b.shape[-2:] != (n, n):
@@ -207,6 +219,8 @@ def product_state_cov(amplitudes: torch.Tensor, extended: bool = False) -> torch
 # ------------------------------------------------------------------------------------------------ covariance
 def cov_basis(x: torch.Tensor, n_qubits: int, bits: Optional[torch.Tensor] = None) -> torch.Tensor:
     """cov[b] = X_b^T Lambda_0(bits) X_b for X (B, d, m)."""
+    if _ag.needs_grad(x):
+        return _ag.CovBasis.apply(x, n_qubits, bits)
     x = _f64(x, "x")
     B, d, m = x.shape
     if d != 2 * n_qubits:
@@ -219,6 +233,9 @@ def cov_basis(x: torch.Tensor, n_qubits: int, bits: Optional[torch.Tensor] = Non
 
 def cov_dense(r: torch.Tensor, l0: torch.Tensor, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
     """cov[b] = (R~_b^T L0 R~_b)[idx, idx]; L0 is (D,D) or (B,D,D) with D = d or d+1 (extended covariance)."""
+    if _ag.needs_grad(r, l0):
+        raise NotImplementedError("cov_dense has no adjoint kernel yet: gradients are available for basis-state inputs "
+                                  "(cov_basis) only")
     r, l0 = _f64(r, "r"), _f64(l0, "l0")
     if r.ndim == 2:
         r = r[None]
@@ -245,6 +262,8 @@ def cov_dense(r: torch.Tensor, l0: torch.Tensor, idx: Optional[torch.Tensor] = N
 # ------------------------------------------------------------------------------------------------ Pfaffians
 def pfaffian(a: torch.Tensor, signed: bool = False, scale: float = 1.0) -> torch.Tensor:
     """Batched Pfaffian of real skew-symmetric matrices (..., m, m) -> (...)."""
+    if _ag.needs_grad(a):
+        return _ag.Pfaffian.apply(a, signed, scale)
     a = _f64(a, "a")
     m = a.shape[-1]
     if a.shape[-2] != m:
@@ -261,6 +280,9 @@ def pfaffian(a: torch.Tensor, signed: bool = False, scale: float = 1.0) -> torch
 
 def probs(cov: torch.Tensor, outcomes: torch.Tensor, normalize: bool = False) -> torch.Tensor:
     """out[b, q] = 2^-k |Pf(cov[b] + Lambda_y(outcomes[q]))|; cov (B, 2k, 2k), outcomes (Q, k)."""
+    if _ag.needs_grad(cov):
+        p = _ag.Probs.apply(cov, outcomes)
+        return p / p.sum(dim=1, keepdim=True) if normalize else p
     cov = _f64(cov, "cov")
     outcomes = outcomes.to(device=cov.device, dtype=torch.int8).contiguous()
     B, m, _ = cov.shape
@@ -274,6 +296,11 @@ def probs(cov: torch.Tensor, outcomes: torch.Tensor, normalize: bool = False) ->
 
 def probs_all(cov: torch.Tensor, normalize: bool = False) -> torch.Tensor:
     """Every outcome of the k measured wires: out[b, q] for q in range(2^k), MSB first; cov (B, 2k, 2k)."""
+    if _ag.needs_grad(cov):  # the elimination tree has no adjoint; enumerate the outcomes (states_to_binary order)
+        k = cov.shape[-1] // 2
+        q = torch.arange(1 << k, device=cov.device)
+        outcomes = ((q[:, None] >> torch.arange(k - 1, -1, -1, device=cov.device)[None, :]) & 1).to(torch.int8)
+        return probs(cov, outcomes, normalize)
     cov = _f64(cov, "cov")
     B, m, _ = cov.shape
     k = m // 2
@@ -288,6 +315,8 @@ def probs_all(cov: torch.Tensor, normalize: bool = False) -> torch.Tensor:
 
 def sector_features(cov: torch.Tensor, index_sets: torch.Tensor) -> torch.Tensor:
     """feats[b, t] = Pf(cov[b][S_t, S_t]); cov (B, D, D), index_sets (T, s)."""
+    if _ag.needs_grad(cov):
+        return _ag.SectorFeatures.apply(cov, index_sets)
     cov = _f64(cov, "cov")
     index_sets = index_sets.to(device=cov.device, dtype=torch.int32).contiguous()
     B, D, _ = cov.shape
@@ -299,6 +328,9 @@ def sector_features(cov: torch.Tensor, index_sets: torch.Tensor) -> torch.Tensor
 
 def rowdot(feats: torch.Tensor, coeffs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b] (+)= sum_t feats[b,t] coeffs[t] (accumulates when ``out`` is given)."""
+    if _ag.needs_grad(feats, out):  # linear: autograd's own matvec is the adjoint
+        r = feats.to(torch.float64) @ coeffs.to(device=feats.device, dtype=torch.float64)
+        return r if out is None else out + r
     feats = _f64(feats, "feats")
     coeffs = _f64(coeffs.to(feats.device), "coeffs")
     B, T = feats.shape
@@ -312,6 +344,8 @@ def rowdot(feats: torch.Tensor, coeffs: torch.Tensor, out: Optional[torch.Tensor
 def pauli_sum_small(cov: torch.Tensor, term_ptr: torch.Tensor, indices: torch.Tensor, coeffs: torch.Tensor,
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b] (+)= sum_t coeffs[t] Pf(cov[b][S_t, S_t]) for index sets of mixed sizes <= 6 (one launch)."""
+    if _ag.needs_grad(cov, out):
+        raise NotImplementedError("pauli_sum_small is inference-only; use sector_features + rowdot under autograd")
     cov = _f64(cov, "cov")
     B, D = cov.shape[0], cov.shape[-1]
     term_ptr = term_ptr.to(device=cov.device, dtype=torch.int32).contiguous()
@@ -329,9 +363,36 @@ def pauli_sum_small(cov: torch.Tensor, term_ptr: torch.Tensor, indices: torch.Te
 
 
 # ------------------------------------------------------------------------------------------------ Gram
+def _gram_differentiable(cov0, cov1, scale, mode, row_range):
+    """Training-size Gram under autograd (kernel alignment, ml/kernels/kernel.py:200-283): the evaluated cells are
+    batched Pfaffians of cov0[i] + cov1[j] through the differentiable Pfaffian op; cell selection, mirroring and the
+    unit diagonal follow gram_matrix.py:127-161,191-195."""
+    n0, n1 = cov0.shape[0], cov1.shape[0]
+    rb, re = (0, n0) if row_range is None else row_range
+    dev = cov0.device
+    ii, jj = torch.meshgrid(torch.arange(rb, re, device=dev), torch.arange(n1, device=dev), indexing="ij")
+    if mode == GRAM_FULL:
+        keep = torch.ones_like(ii, dtype=torch.bool)
+    else:
+        keep = (jj > ii) if n0 < n1 else (ii > jj)
+    ii, jj = ii[keep], jj[keep]
+    vals = pfaffian(cov0[ii] + cov1[jj], signed=False, scale=scale)
+    K = torch.zeros((n0, n1), dtype=torch.float64, device=dev).index_put((ii, jj), vals)
+    if mode == GRAM_REFERENCE:
+        q = min(n0, n1)
+        mirror = (jj < n0) & (ii < n1)
+        K = K.index_put((jj[mirror], ii[mirror]), vals[mirror])
+        eye = torch.zeros_like(K)
+        eye[torch.arange(q, device=dev), torch.arange(q, device=dev)] = 1.0
+        K = K + eye
+    return K
+
+
 def gram(cov0: torch.Tensor, cov1: torch.Tensor, scale: float, mode: int = GRAM_REFERENCE,
          row_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """K[i, j] = scale |Pf(cov0[i] + cov1[j])| with the reference's triangle/mirror/unit-diagonal rules."""
+    if _ag.needs_grad(cov0, cov1):
+        return _gram_differentiable(cov0, cov1, scale, mode, row_range)
     cov0, cov1 = _f64(cov0, "cov0"), _f64(cov1, "cov1")
     n0, d, _ = cov0.shape
     n1 = cov1.shape[0]

@@ -192,7 +192,7 @@ def test_kernel_gram_equals_reference_formulation(n, nf, rot, ent):
     k.float32_gram = False
     k.fit(x0)
     o = kernels.FermionicPQCKernelOracle(n_qubits=n, rotations=rot, entangling_mth=ent).fit(x0)
-    np.testing.assert_array_equal(k.bias_, o.bias_)
+    np.testing.assert_array_equal(k.bias_.detach().cpu().numpy(), o.bias_)
     assert k.depth_ == o.depth_
     np.testing.assert_allclose(k._x_to_sptm(x0).cpu().numpy(), o.x_to_sptm(x0), rtol=RTOL, atol=ATOL)
     np.testing.assert_allclose(k(x0).cpu().numpy(), o.gram(x0, float32_store=False), rtol=RTOL, atol=ATOL)
