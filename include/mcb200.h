@@ -217,6 +217,18 @@ void mcb200_reset_launch_count(void);
  * (kind 0) or a DMMA m8n8k4 loop (kind 1) and returns achieved TFLOP/s (< 0 on error). */
 double mcb200_probe_fp64_tflops(int32_t kind, int32_t iters, void* stream);
 
+/* Computational-basis sampling on the device.  cov (B, 2k, 2k) is the evolved covariance
+ * restricted to the k sampled wires; every (shot, instance) pair draws y in {0,1}^k from p(y) = 2^-k |Pf(cov + Lambda_y)|
+ * by the chain rule p(y) = prod_j p(y_j | y_<j), the conditionals being the pivots of a pivot-free elimination
+ * (csrc/sampling.cu).  out_bits (shots, B, k) int8 and/or out_prob (shots, B) = prod_j p(y_j | y_<j) = p(y).
+ * forced_bits (shots, B, k) != NULL: nothing is drawn, the given strings are followed (evaluates p of known strings).
+ * The stream of uniforms is a counter-based hash of (seed, shot * B + b, j): results do not depend on the launch shape.
+ * Replaces KQubitsByKQubitsSampling.batch_generate_samples_by_subsets_of_k
+ * (devices/sampling_strategies/k_qubits_by_k_qubits_sampling.py:121-176) + random_index (utils/math.py:230-300) +
+ * the get_states_probability calls they issue per step (devices/nif_device.py:705-723,742-810). */
+int mcb200_sample(const double* cov, int64_t B, int32_t k, int64_t shots, uint64_t seed, const int8_t* forced_bits,
+                  int8_t* out_bits, double* out_prob, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Reverse-mode derivatives.  The reference differentiates this path with torch autograd
  * (devices/nif_device.py:949-989 advertises backprop; ml/kernels/kernel.py:200-283 trains through the Gram; the

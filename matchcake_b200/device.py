@@ -114,8 +114,13 @@ class NonInteractingFermionicDevice:
         if wires is not None:
             n = wires if isinstance(wires, (int, np.integer)) else len(list(wires))
             assert n > 1, "At least two wires are required for this device."
-        if shots is not None:
-            raise NotImplementedError("Shot-based sampling is outside the B200 hot path (SURVEY.md 8f rank 3).")
+        if shots is not None and (not isinstance(shots, (int, np.integer)) or shots < 1):
+            raise ValueError(f"shots must be a positive integer or None, got {shots!r}")
+        self._shots = None if shots is None else int(shots)
+        self._current_shots: Optional[int] = None
+        self._samples = None
+        self.sampling_seed = kwargs.get("seed", 0)
+        self._sample_calls = 0
         self._wires: Optional[Tuple] = None
         if wires is not None:
             self._wires = tuple(range(wires)) if isinstance(wires, (int, np.integer)) else _wires_tuple(wires)
@@ -161,7 +166,11 @@ class NonInteractingFermionicDevice:
 
     @property
     def shots(self):
-        return None
+        return self._active_shots
+
+    @property
+    def _active_shots(self) -> Optional[int]:
+        return self._current_shots if self._current_shots is not None else self._shots
 
     @property
     def state_prep_op(self):
@@ -178,6 +187,7 @@ class NonInteractingFermionicDevice:
         self._sptm = None
         self._compiled = None
         self._batched = False
+        self._samples = None
         self.apply_metadata = defaultdict()
         if self._wires is not None:
             self._state_prep_op = ProductState.from_basis_state(np.zeros(self.num_wires, dtype=int), wires=self.wires)
@@ -624,6 +634,37 @@ class NonInteractingFermionicDevice:
     def probability(self, wires=None, shot_range=None, bin_size=None):
         return self.analytic_probability(wires=wires if wires is not None and len(_wires_tuple(wires)) else self.wires)
 
+    # ------------------------------------------------------------------ sampling
+    def generate_samples(self, shots: Optional[int] = None, wires=None, seed: Optional[int] = None,
+                         return_prob: bool = False):
+        """Computational-basis samples ``(shots, *batch, n_wires)`` as a numpy integer array, q_0 first (:705-723).
+
+        The reference walks the chain rule wire block by wire block on the host, asking the device for prefix
+        probabilities at every step (KQubitsByKQubitsSampling); here one kernel launch draws every (shot, instance)
+        string from the conditionals of a pivot-free elimination of the evolved covariance (csrc/sampling.cu).  The
+        stream of uniforms is a counter-based hash of ``seed`` (``device.sampling_seed`` advanced per call)."""
+        shots = self._active_shots if shots is None else shots
+        if shots is None:
+            raise ValueError("The number of shots must be specified to generate samples.")
+        wires = self.wires if wires is None else _wires_tuple(wires)
+        widx = np.array([self._wire_index(w) for w in wires], dtype=int)
+        maj = np.stack([2 * widx, 2 * widx + 1], axis=1).ravel()
+        self._compile()
+        with torch.no_grad():
+            cov = self._cov_device(maj)
+        if seed is None:
+            seed = (int(self.sampling_seed) * 0x9E3779B1 + self._sample_calls) & 0xFFFFFFFFFFFFFFFF
+            self._sample_calls += 1
+        res = _ops.sample(cov, int(shots), seed=seed, return_prob=return_prob)
+        bits, prob = res if return_prob else (res, None)
+        batched = self._batched or self._state_prep_op.batch_size is not None
+        out = bits.cpu().numpy().astype(np.int64)
+        if not batched:
+            out = out[:, 0]
+        if return_prob:
+            return out, self._out(prob if batched else prob[:, 0])
+        return out
+
     # ------------------------------------------------------------------ expectation values
     def _expval_pauli_device(self, observable) -> torch.Tensor:
         n = self.num_wires
@@ -687,14 +728,22 @@ class NonInteractingFermionicDevice:
                        shots: Any = _UNSET, **kwargs):
         if output_type is None:
             return None
-        if shots is not _UNSET and shots is not None:
-            raise NotImplementedError("Shot-based outputs are outside the B200 hot path.")
+        if shots is not _UNSET:  # per-call override, like nif_device.py:657-660
+            if shots != self._current_shots:
+                self._samples = None
+            self._current_shots = shots
+        if output_type == "samples":
+            if self._active_shots is None:
+                raise ValueError("The number of shots must be specified to generate samples.")
+            if self._samples is None:
+                self._samples = self.generate_samples()
+            return self._samples
         if output_type == "expval":
             return self.expval(observable)
         if output_type == "probs":
             return self.probability(wires=kwargs.get("wires", None))
-        if output_type in ("samples", "star_state", "*state"):
-            raise NotImplementedError(f"Output type {output_type} (sampling) is outside the B200 hot path.")
+        if output_type in ("star_state", "*state"):
+            raise NotImplementedError(f"Output type {output_type} (star-state search) is outside the B200 hot path.")
         raise ValueError(f"Output type {output_type} is not supported.")
 
 

@@ -313,6 +313,31 @@ def probs_all(cov: torch.Tensor, normalize: bool = False) -> torch.Tensor:
     return out
 
 
+def sample(cov: torch.Tensor, shots: int, seed: int = 0, forced_bits: Optional[torch.Tensor] = None,
+           return_prob: bool = False):
+    """Draw ``shots`` bit strings per instance from p(y) = 2^-k |Pf(cov + Lambda_y)|; cov (B, 2k, 2k).
+
+    Returns int8 ``(shots, B, k)`` (and the probability of every drawn string ``(shots, B)`` with ``return_prob``).
+    With ``forced_bits`` (shots, B, k) nothing is drawn: the probabilities of the given strings are returned."""
+    cov = _f64(cov.detach(), "cov")
+    B, m, _ = cov.shape
+    k = m // 2
+    if m != 2 * k or k < 1:
+        raise ValueError("cov must be (B, 2k, 2k)")
+    fb = None
+    if forced_bits is not None:
+        fb = forced_bits.to(device=cov.device, dtype=torch.int8).contiguous()
+        if tuple(fb.shape) != (shots, B, k):
+            raise ValueError(f"forced_bits must have shape {(shots, B, k)}, got {tuple(fb.shape)}")
+    bits = torch.empty((shots, B, k), dtype=torch.int8, device=cov.device) if fb is None else None
+    prob = torch.empty((shots, B), dtype=torch.float64, device=cov.device) if (return_prob or fb is not None) else None
+    check(_lib.load().mcb200_sample(_ptr(cov), B, k, shots, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(fb), _ptr(bits),
+                                    _ptr(prob), _stream()))
+    if fb is not None:
+        return prob
+    return (bits, prob) if return_prob else bits
+
+
 def sector_features(cov: torch.Tensor, index_sets: torch.Tensor) -> torch.Tensor:
     """feats[b, t] = Pf(cov[b][S_t, S_t]); cov (B, D, D), index_sets (T, s)."""
     if _ag.needs_grad(cov):
