@@ -115,8 +115,11 @@ __device__ __forceinline__ void tiles_update_from(double (&c)[Tiles<MT>::NT][2],
 // c: fragments of the upper tiles (entries at rows/cols >= m must be 0); with SR > 0 the tiles of the first SR
 // tile-rows are read from / written to sm (this lane's slot, see tile_get) instead.  scratch: Tiles<MT>::kScratch
 // doubles private to the warp.  Returns the signed Pfaffian in every lane.
+// `start` (even): rows/columns below it have already been eliminated (by warp_pfaffian_static_steps); the result is
+// then the Pfaffian of the remaining Schur complement.
 template <int MT, int SR = 0>
-__device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, double* scratch, double2* sm = nullptr) {
+__device__ double warp_pfaffian_tiles_pivoted(double (&c)[Tiles<MT>::NT][2], int m, double* scratch,
+                                              double2* sm = nullptr, int start = 0) {
   using T = Tiles<MT>;
   constexpr int H = (T::M + 31) / 32;  // vector entries / pivot candidates per lane
   const int lane = lane_id(), gr = lane >> 2, tg = lane & 3;
@@ -141,11 +144,16 @@ __device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, doub
   // active set as two 32-bit words (uniform) + this lane's own entries j = lane, lane + 32
   unsigned act_lo = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
   unsigned act_hi = (m >= 64) ? 0xffffffffu : ((m > 32) ? ((1u << (m - 32)) - 1u) : 0u);
-  bool on0 = lane < m, on1 = lane + 32 < m;
+  if (start > 0) {
+    const unsigned long long keep = ~((1ull << start) - 1ull);
+    act_lo &= (unsigned)keep;
+    act_hi &= (unsigned)(keep >> 32);
+  }
+  bool on0 = lane < m && lane >= start, on1 = lane + 32 < m && lane + 32 >= start;
   const int j1 = (lane + 32 < T::M) ? lane + 32 : lane;  // second entry of this lane (only used when on1)
   double pf = 1.0;
   unsigned parity = 0;
-  const int steps = m >> 1;
+  const int steps = (m - start) >> 1;
   for (int s = 0; s < steps; ++s) {
     const int r = act_lo ? (__ffs((int)act_lo) - 1) : (31 + __ffs((int)act_hi));
     const int tr = r >> 3;
@@ -231,6 +239,95 @@ __device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, doub
     __syncwarp();
   }
   return (parity & 1u) ? -pf : pf;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Static-order fast path.  Step S eliminates rows/columns (2S, 2S+1) with pivot A[2S][2S+1] -- no search, no
+// permutation, every tile / lane index is a compile-time constant, so a step is: 2 predicated row stores, one
+// reciprocal, 2 loads + 2 multiplies per live tile index and one DMMA per live tile (~4x fewer instructions than the
+// pivoted step).  For the matrices of this path (Lambda|_W + Lambda_y, Lambda_i + Lambda_j) the natural pivot is the
+// conditional probability of the target outcome and is rarely small.  A guard keeps the accuracy of partial pivoting:
+// the step is taken only if |pivot| >= kStaticPivotRatio * max_j |A[2S][j]| (multipliers <= 1/ratio); otherwise the
+// routine stops and reports how many indices it eliminated, and the pivoted routine finishes the remaining Schur
+// complement (warp_pfaffian_tiles_pivoted(..., start)).
+constexpr double kStaticPivotRatio = 1e-3;
+
+template <int MT, int SR, int TR, int TJ>
+__device__ __forceinline__ void static_store_rows(const double (&c)[Tiles<MT>::NT][2], const double2* sm, double* dst) {
+  if constexpr (TJ < MT) {
+    *reinterpret_cast<double2*>(dst + 8 * TJ) = tile_get<MT, SR, TR, TJ>(c, sm);
+    static_store_rows<MT, SR, TR, TJ + 1>(c, sm, dst);
+  }
+}
+
+// Returns the number of eliminated indices (m when the whole matrix went through); pf is multiplied by the pivots.
+template <int MT, int SR, int S = 0>
+__device__ __forceinline__ int warp_pfaffian_static_steps(double (&c)[Tiles<MT>::NT][2], int m, double* scratch,
+                                                          double2* sm, double& pf) {
+  using T = Tiles<MT>;
+  if constexpr (2 * S >= T::M) {
+    return m;
+  } else {
+    constexpr int R = 2 * S, Q = R + 1, TR = R >> 3;
+    if (R >= m) return m;
+    const int lane = lane_id(), gr = lane >> 2, tg = lane & 3;
+    double* ubuf = scratch + 2 * T::M;   // row R
+    double* vbuf = ubuf + T::kVec;       // row Q
+    // (1) rows R and Q of the tile row TR -> shared vectors (lanes holding them: gr == R & 7 / gr == Q & 7)
+    if ((gr >> 1) == (S & 3)) static_store_rows<MT, SR, TR, TR>(c, sm, ((gr & 1) ? vbuf : ubuf) + 2 * tg);
+    __syncwarp();
+    const double piv = ubuf[Q];
+    // (2) guard: largest |A[R][j]|, j > Q, from the high words (entries >= m are zero)
+    unsigned key = 0u;
+    if constexpr (Q < 31) {
+      if (lane > Q) key = (unsigned)__double2hiint(ubuf[lane]) & 0x7fffffffu;
+    }
+    if constexpr (T::M > 32) {
+      if (lane + 32 < T::M && lane + 32 > Q) {
+        const unsigned k2 = (unsigned)__double2hiint(ubuf[lane + 32]) & 0x7fffffffu;
+        key = k2 > key ? k2 : key;
+      }
+    }
+    const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+    if (!(fabs(piv) >= kStaticPivotRatio * __hiloint2double((int)kmax, 0)) || piv == 0.0) return R;
+    pf *= piv;
+    if (R + 2 >= m) return m;  // last pair: nothing left to update
+    // (3) fragments of A += w tau^T - tau w^T, tau = u / piv, w = row Q:
+    //     A-fragment columns (w/2, -tau/2, w/2, -tau/2), B-fragment rows (tau; w; tau; w)
+    const double inv = 1.0 / piv;
+    const bool odd = tg & 1;
+    const double sa = odd ? -0.5 * inv : 0.5, sb = odd ? 1.0 : inv;
+    const double* srcA = (odd ? ubuf : vbuf) + gr;
+    const double* srcB = (odd ? vbuf : ubuf) + gr;
+    double af[MT], bf[MT];
+#pragma unroll
+    for (int t = TR; t < MT; ++t) {
+      af[t] = sa * srcA[8 * t];
+      bf[t] = sb * srcB[8 * t];
+    }
+    if (gr <= (Q & 7)) {  // indices <= Q of the pivot tile are dead: they neither change nor contribute
+      af[TR] = 0.0;
+      bf[TR] = 0.0;
+    }
+    // (4) one DMMA per live upper tile; tile row TR is dead once its last pair has been eliminated
+    constexpr int TI0 = ((S & 3) == 3) ? TR + 1 : TR;
+    tiles_update_from<MT, SR, TI0>(c, sm, af, bf);
+    __syncwarp();
+    return warp_pfaffian_static_steps<MT, SR, S + 1>(c, m, scratch, sm, pf);
+  }
+}
+
+// c: fragments of the upper tiles (entries at rows/cols >= m must be 0); with SR > 0 the tiles of the first SR
+// tile-rows are read from / written to sm (this lane's slot, see tile_get) instead.  scratch: Tiles<MT>::kScratch
+// doubles private to the warp.  Returns the signed Pfaffian in every lane.
+template <int MT, int SR = 0>
+__device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, double* scratch, double2* sm = nullptr) {
+  if (m == 0) return 1.0;
+  if (m & 1) return 0.0;
+  double pf = 1.0;
+  const int done = warp_pfaffian_static_steps<MT, SR>(c, m, scratch, sm, pf);
+  if (done < m) pf *= warp_pfaffian_tiles_pivoted<MT, SR>(c, m, scratch, sm, done);
+  return pf;
 }
 
 }  // namespace mcb200
