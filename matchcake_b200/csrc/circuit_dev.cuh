@@ -23,43 +23,20 @@ __device__ __forceinline__ double load_angle(const CircuitDev& c, const double* 
 }
 
 __device__ __forceinline__ void gate_coefficients(const CircuitDev& c, const mcb200_gate_t& g, const double* prow, double* out) {
-  switch (g.kind) {
-    case MCB200_GATE_RXRX: {  // sptm_comp_rxrx.py:48-57
-      double th = load_angle(c, prow, g.off) / 2, ph = load_angle(c, prow, g.off + 1) / 2;
-      double s, co;
-      sincos(ph - th, &s, &co);  // rows (0,3)
-      out[0] = co;
-      out[1] = -s;
-      sincos(ph + th, &s, &co);  // rows (1,2)
-      out[2] = co;
-      out[3] = s;
-      break;
-    }
-    case MCB200_GATE_RYRY: {  // sptm_comp_ryry.py:53-67
-      double th = load_angle(c, prow, g.off), ph = load_angle(c, prow, g.off + 1);
-      double s, co;
-      sincos((th + ph) / 2, &s, &co);  // rows (0,2)
-      out[0] = co;
-      out[1] = -s;
-      sincos((th - ph) / 2, &s, &co);  // rows (1,3)
-      out[2] = co;
-      out[3] = s;
-      break;
-    }
-    case MCB200_GATE_RZRZ: {  // sptm_comp_rzrz.py:51-67 (imaginary parts are identically ~0)
-      double th = load_angle(c, prow, g.off), ph = load_angle(c, prow, g.off + 1);
-      double s, co;
-      sincos((th + ph) / 2, &s, &co);  // rows (0,1)
-      out[0] = co;
-      out[1] = s;
-      sincos((th - ph) / 2, &s, &co);  // rows (2,3)
-      out[2] = co;
-      out[3] = s;
-      break;
-    }
-    default:
-      break;
-  }
+  if (g.kind > MCB200_GATE_RZRZ) return;
+  // every kind needs exactly cos/sin of the half sum and the half difference of its two angles (no divergent trig):
+  //   RXRX pairs (0,3): cos/-sin((p1-p0)/2), (1,2): cos/sin((p1+p0)/2)      sptm_comp_rxrx.py:48-57
+  //   RYRY pairs (0,2): cos/-sin((p0+p1)/2), (1,3): cos/sin((p0-p1)/2)      sptm_comp_ryry.py:53-67
+  //   RZRZ pairs (0,1): cos/ sin((p0+p1)/2), (2,3): cos/sin((p0-p1)/2)      sptm_comp_rzrz.py:51-67 (imaginary parts ~0)
+  const double p0 = load_angle(c, prow, g.off), p1 = load_angle(c, prow, g.off + 1);
+  double ss, cs, sd, cd;
+  sincos(p0 / 2 + p1 / 2, &ss, &cs);
+  sincos(p0 / 2 - p1 / 2, &sd, &cd);
+  const bool x = g.kind == MCB200_GATE_RXRX, y = g.kind == MCB200_GATE_RYRY;
+  out[0] = x ? cd : cs;
+  out[1] = x ? sd : (y ? -ss : ss);
+  out[2] = x ? cs : cd;
+  out[3] = x ? ss : sd;
 }
 
 // x <- G x on rows 2*wire0 .. of the columns cc = first, first + step, ... < mc of X (one gate, many columns).

@@ -36,29 +36,18 @@ __device__ __forceinline__ double wc_angle(const WarpCircuit& c, const double* p
 __device__ __forceinline__ void wc_rotation_coef(const WarpCircuit& c, const mcb200_gate_t& g, const double* prow,
                                                  double* out) {
   const double p0 = wc_angle(c, prow, g.off), p1 = wc_angle(c, prow, g.off + 1);
-  double a1, a2, s, co;
-  if (g.kind == MCB200_GATE_RXRX) {          // pairs (0,3): cos/-sin(phi-theta); (1,2): cos/sin(phi+theta)
-    a1 = p1 / 2 - p0 / 2;
-    a2 = p1 / 2 + p0 / 2;
-    sincos(a1, &s, &co);
-    out[0] = co;
-    out[1] = -s;
-  } else if (g.kind == MCB200_GATE_RYRY) {   // pairs (0,2): cos/-sin((t+p)/2); (1,3): cos/sin((t-p)/2)
-    a1 = (p0 + p1) / 2;
-    a2 = (p0 - p1) / 2;
-    sincos(a1, &s, &co);
-    out[0] = co;
-    out[1] = -s;
-  } else {                                   // RZRZ pairs (0,1): cos/sin((t+p)/2); (2,3): cos/sin((t-p)/2)
-    a1 = (p0 + p1) / 2;
-    a2 = (p0 - p1) / 2;
-    sincos(a1, &s, &co);
-    out[0] = co;
-    out[1] = s;
-  }
-  sincos(a2, &s, &co);
-  out[2] = co;
-  out[3] = s;
+  // every kind needs exactly cos/sin of the half sum and the half difference (no divergent trig):
+  //   RXRX pairs (0,3): cos/-sin((p1-p0)/2), (1,2): cos/sin((p1+p0)/2)      sptm_comp_rxrx.py:48-57
+  //   RYRY pairs (0,2): cos/-sin((p0+p1)/2), (1,3): cos/sin((p0-p1)/2)      sptm_comp_ryry.py:53-67
+  //   RZRZ pairs (0,1): cos/ sin((p0+p1)/2), (2,3): cos/sin((p0-p1)/2)      sptm_comp_rzrz.py:51-67
+  double ss, cs, sd, cd;
+  sincos(p0 / 2 + p1 / 2, &ss, &cs);
+  sincos(p0 / 2 - p1 / 2, &sd, &cd);
+  const bool x = g.kind == MCB200_GATE_RXRX, y = g.kind == MCB200_GATE_RYRY;
+  out[0] = x ? cd : cs;
+  out[1] = x ? sd : (y ? -ss : ss);
+  out[2] = x ? cs : cd;
+  out[3] = x ? ss : sd;
 }
 
 // Compact per-gate code built once per block: kind | wire0 << 3 | wire1 << 11 | transpose << 19 | run << 20, where
@@ -70,7 +59,7 @@ __device__ __forceinline__ int wc_wire1(int code) { return (code >> 11) & 0xff; 
 __device__ __forceinline__ int wc_run(int code) { return (code >> 20) & 0xfff; }
 
 template <int MT>
-__global__ void __launch_bounds__(192) expval_warp_kernel(WarpCircuit wc, const double* __restrict__ params,
+__global__ void __launch_bounds__(192, (MT <= 4 ? 3 : 1)) expval_warp_kernel(WarpCircuit wc, const double* __restrict__ params,
                                                           long long B, const int8_t* init_bits,
                                                           const int8_t* target_bits, int gates_in_smem,
                                                           double* __restrict__ out) {
@@ -257,7 +246,7 @@ __global__ void __launch_bounds__(192) expval_warp_kernel(WarpCircuit wc, const 
         }
       }
     }
-    const double pf = warp_pfaffian_tiles<MT>(c, d, scratch);
+    const double pf = warp_pfaffian_tiles<MT, 0, true>(c, d, scratch);  // Lambda|_W + Lambda_y of a physical state: bounded
     if (lane == 0) out[b] = ldexp(fabs(pf), -n);
     __syncwarp();
   }
