@@ -242,10 +242,10 @@ __device__ double warp_pfaffian_tiles_pivoted(double (&c)[Tiles<MT>::NT][2], int
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Static-order fast path.  Step S eliminates rows/columns (2S, 2S+1) with pivot A[2S][2S+1] -- no search, no
-// permutation, every tile / lane index is a compile-time constant, so a step is: 2 predicated row stores, one
-// reciprocal, 2 loads + 2 multiplies per live tile index and one DMMA per live tile (~4x fewer instructions than the
-// pivoted step).  For the matrices of this path (Lambda|_W + Lambda_y, Lambda_i + Lambda_j) the natural pivot is the
+// Static-order fast path.  Pair S = (2S, 2S+1) is eliminated with pivot A[2S][2S+1] -- no search, no permutation,
+// every tile / lane index is a compile-time constant, so a step is: predicated row stores, a reciprocal, 2 loads + 2
+// multiplies per live tile index and one DMMA per live tile (several times fewer instructions than the pivoted
+// step), and two pairs share one pass over the tiles (rank-4 update, see warp_pfaffian_static_steps).  For the matrices of this path (Lambda|_W + Lambda_y, Lambda_i + Lambda_j) the natural pivot is the
 // conditional probability of the target outcome and is rarely small.  A guard keeps the accuracy of partial pivoting:
 // the step is taken only if |pivot| >= kStaticPivotRatio * max_j |A[2S][j]| (multipliers <= 1/ratio); otherwise the
 // routine stops and reports how many indices it eliminated, and the pivoted routine finishes the remaining Schur
@@ -271,67 +271,109 @@ __device__ __forceinline__ void static_store_rows(const double (&c)[Tiles<MT>::N
   }
 }
 
-// Returns the number of eliminated indices (m when the whole matrix went through); pf is multiplied by the pivots.
-// BOUNDED: the caller guarantees |A[i][j]| <= 2 for the matrix and all its Schur complements (Lambda|_W + Lambda_y of a
-// physical state: the conditional covariance after each projected wire is again a covariance), so the guard compares
-// the pivot with the bound instead of searching the row maximum.
-template <int MT, int SR, bool BOUNDED = false, int S = 0>
+// Guard of one static pivot: |piv| against the largest |row[j]|, j > last (or against the bound 2 when BOUNDED: the
+// caller guarantees |A[i][j]| <= 2 for the matrix and all its Schur complements -- Lambda|_W + Lambda_y of a physical
+// state, whose conditional covariance after each projected wire is again a covariance).
+template <int M, bool BOUNDED>
+__device__ __forceinline__ bool static_pivot_ok(double piv, const double* row, int last) {
+  if constexpr (BOUNDED) {
+    return fabs(piv) >= 2.0 * kStaticPivotRatio;
+  } else {
+    const int lane = lane_id();
+    unsigned key = 0u;
+    if (lane > last && lane < M) key = (unsigned)__double2hiint(row[lane]) & 0x7fffffffu;
+    if constexpr (M > 32) {
+      if (lane + 32 < M && lane + 32 > last) {
+        const unsigned k2 = (unsigned)__double2hiint(row[lane + 32]) & 0x7fffffffu;
+        key = k2 > key ? k2 : key;
+      }
+    }
+    const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+    return fabs(piv) >= kStaticPivotRatio * __hiloint2double((int)kmax, 0) && piv != 0.0;
+  }
+}
+
+// Double step D eliminates the pairs (4D, 4D+1) and (4D+2, 4D+3) and applies BOTH rank-2 updates to the trailing tiles
+// as one K = 4 DMMA per tile:  A += w tau^T - tau w^T + w' tau'^T - tau' w'^T  with
+//   A-fragment columns (w, -tau, w', -tau'),  B-fragment rows (tau; w; tau'; w')
+// (tau = row 4D / piv1, w = row 4D+1; tau', w' the same for rows 4D+2, 4D+3 AFTER the first pair's update, which is
+// applied to those two rows only, as vectors in shared memory).  Half the tensor instructions of two rank-2 steps and
+// no wasted K lanes.  Returns the number of eliminated indices (m when the whole matrix went through); pf is
+// multiplied by the pivots taken.
+template <int MT, int SR, bool BOUNDED = false, int D = 0>
 __device__ __forceinline__ int warp_pfaffian_static_steps(double (&c)[Tiles<MT>::NT][2], int m, double* scratch,
                                                           double2* sm, double& pf) {
   using T = Tiles<MT>;
-  if constexpr (2 * S >= T::M) {
+  if constexpr (4 * D >= T::M) {
     return m;
   } else {
-    constexpr int R = 2 * S, Q = R + 1, TR = R >> 3;
+    constexpr int R = 4 * D, TR = R >> 3;
+    constexpr int VS = T::M + 4;  // vector stride: the 4 vectors start 4 doubles apart modulo a 128-byte bank line
     if (R >= m) return m;
     const int lane = lane_id(), gr = lane >> 2, tg = lane & 3;
-    double* ubuf = scratch + 2 * T::M;   // row R
-    double* vbuf = ubuf + T::kVec;       // row Q
-    // (1) rows R and Q of the tile row TR -> shared vectors (lanes holding them: gr == R & 7 / gr == Q & 7)
-    if ((gr >> 1) == (S & 3)) static_store_rows<MT, SR, TR, TR>(c, sm, ((gr & 1) ? vbuf : ubuf) + 2 * tg);
+    double* u = scratch;         // row R
+    double* v = u + VS;          // row R + 1
+    double* u2 = v + VS;         // row R + 2
+    double* v2 = u2 + VS;        // row R + 3
+    // (1) rows R .. R+3 of tile row TR -> shared vectors (held by the lanes with gr >> 2 == D & 1)
+    if ((gr >> 2) == (D & 1)) static_store_rows<MT, SR, TR, TR>(c, sm, scratch + (gr & 3) * VS + 2 * tg);
     __syncwarp();
-    const double piv = ubuf[Q];
-    if constexpr (BOUNDED) {
-      if (!(fabs(piv) >= 2.0 * kStaticPivotRatio)) return R;
-    } else {
-      // (2) guard: largest |A[R][j]|, j > Q, from the high words (entries >= m are zero)
-      unsigned key = 0u;
-      if constexpr (Q < 31) {
-        if (lane > Q) key = (unsigned)__double2hiint(ubuf[lane]) & 0x7fffffffu;
-      }
-      if constexpr (T::M > 32) {
-        if (lane + 32 < T::M && lane + 32 > Q) {
-          const unsigned k2 = (unsigned)__double2hiint(ubuf[lane + 32]) & 0x7fffffffu;
-          key = k2 > key ? k2 : key;
+    const double piv1 = u[R + 1];
+    if (!static_pivot_ok<T::M, BOUNDED>(piv1, u, R + 1)) return R;
+    pf *= piv1;
+    if (R + 2 >= m) return m;  // last pair: nothing left to update
+    const double inv1 = fast_rcp(piv1);
+    // (2) first pair's update on rows R+2, R+3 only:  x[c] += w_a tau_c - tau_a w_c
+    {
+      const double t2 = u[R + 2] * inv1, t3 = u[R + 3] * inv1, w2 = v[R + 2], w3 = v[R + 3];
+#pragma unroll
+      for (int q = 0; q < (T::M + 31) / 32; ++q) {
+        const int cc = lane + 32 * q;
+        if (cc >= R + 2 && cc < T::M) {
+          const double tc = u[cc] * inv1, wc = v[cc];
+          u2[cc] += w2 * tc - t2 * wc;
+          v2[cc] += w3 * tc - t3 * wc;
         }
       }
-      const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
-      if (!(fabs(piv) >= kStaticPivotRatio * __hiloint2double((int)kmax, 0)) || piv == 0.0) return R;
     }
-    pf *= piv;
-    if (R + 2 >= m) return m;  // last pair: nothing left to update
-    // (3) fragments of A += w tau^T - tau w^T, tau = u / piv, w = row Q:
-    //     A-fragment columns (w/2, -tau/2, w/2, -tau/2), B-fragment rows (tau; w; tau; w)
-    const double inv = fast_rcp(piv);
+    __syncwarp();
+    const double piv2 = u2[R + 3];
     const bool odd = tg & 1;
-    const double sa = odd ? -0.5 * inv : 0.5, sb = odd ? 1.0 : inv;
-    const double* srcA = (odd ? ubuf : vbuf) + gr;
-    const double* srcB = (odd ? vbuf : ubuf) + gr;
     double af[MT], bf[MT];
+    if (!static_pivot_ok<T::M, BOUNDED>(piv2, u2, R + 3)) {
+      // second pivot rejected: commit the first pair alone (rank-2 update with both K halves carrying it) and stop
+      const double sa = odd ? -0.5 * inv1 : 0.5, sb = odd ? 1.0 : inv1;
+      const double* srcA = (odd ? u : v) + gr;
+      const double* srcB = (odd ? v : u) + gr;
+#pragma unroll
+      for (int t = TR; t < MT; ++t) {
+        af[t] = sa * srcA[8 * t];
+        bf[t] = sb * srcB[8 * t];
+      }
+      if (gr <= ((R + 1) & 7)) af[TR] = bf[TR] = 0.0;
+      tiles_update_from<MT, SR, TR>(c, sm, af, bf);
+      __syncwarp();
+      return R + 2;
+    }
+    pf *= piv2;
+    if (R + 4 >= m) return m;
+    const double inv2 = fast_rcp(piv2);
+    // (3) fragments: lane tg reads vector {w, u, w', u'}[tg] for A and {u, w, u', w'}[tg] for B
+    const double sa = odd ? ((tg & 2) ? -inv2 : -inv1) : 1.0;
+    const double sb = odd ? 1.0 : ((tg & 2) ? inv2 : inv1);
+    const double* srcA = scratch + (tg ^ 1) * VS + gr;
+    const double* srcB = scratch + tg * VS + gr;
 #pragma unroll
     for (int t = TR; t < MT; ++t) {
       af[t] = sa * srcA[8 * t];
       bf[t] = sb * srcB[8 * t];
     }
-    if (gr <= (Q & 7)) {  // indices <= Q of the pivot tile are dead: they neither change nor contribute
-      af[TR] = 0.0;
-      bf[TR] = 0.0;
-    }
-    // (4) one DMMA per live upper tile; tile row TR is dead once its last pair has been eliminated
-    constexpr int TI0 = ((S & 3) == 3) ? TR + 1 : TR;
+    if (gr <= ((R + 3) & 7)) af[TR] = bf[TR] = 0.0;  // indices <= R+3 are dead: they neither change nor contribute
+    // (4) one DMMA per live upper tile; tile row TR is dead once its second quadruple has been eliminated
+    constexpr int TI0 = (D & 1) ? TR + 1 : TR;
     tiles_update_from<MT, SR, TI0>(c, sm, af, bf);
     __syncwarp();
-    return warp_pfaffian_static_steps<MT, SR, BOUNDED, S + 1>(c, m, scratch, sm, pf);
+    return warp_pfaffian_static_steps<MT, SR, BOUNDED, D + 1>(c, m, scratch, sm, pf);
   }
 }
 
