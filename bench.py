@@ -277,7 +277,7 @@ def main():
         metric, unit, scaling = "gram_entries_per_sec", "entries/s", "strong"
         cfg = {"workload": WORKLOADS["c3"], "n_qubits": n, "n_samples": ns, "parallelism": f"Gram rows sharded x{ws}, one all-gather",
                "l2": "per-sample covariances 268 MB > 126 MiB L2"}
-        kernel_name = "gram_tiles_kernel<8,2,4>"
+        kernel_name = "gram_tiles_kernel<8,1,3,4,1>"
         alg_flops_per_launch = gram_flops_per_entry(2 * n) * entries / ws
         launches_per_step = None
         h2d, d2h = ns * 2 * n * 8, ns * ns * 8

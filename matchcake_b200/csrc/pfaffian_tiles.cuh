@@ -311,12 +311,16 @@ __device__ __forceinline__ int warp_pfaffian_static_steps(double (&c)[Tiles<MT>:
     constexpr int VS = T::M + 4;  // vector stride: the 4 vectors start 4 doubles apart modulo a 128-byte bank line
     if (R >= m) return m;
     const int lane = lane_id(), gr = lane >> 2, tg = lane & 3;
-    double* u = scratch;         // row R
-    double* v = u + VS;          // row R + 1
-    double* u2 = v + VS;         // row R + 2
-    double* v2 = u2 + VS;        // row R + 3
+    // row R + k lives in slot brev2(k): consecutive rows are then 8 doubles apart modulo the bank line, so the 16-byte
+    // row stores of a quarter warp (two rows) as well as the 8-byte fragment loads of a half warp (four vectors, four
+    // consecutive entries each) are conflict free
+    double* u = scratch;             // row R
+    double* v = scratch + 2 * VS;    // row R + 1
+    double* u2 = scratch + VS;       // row R + 2
+    double* v2 = scratch + 3 * VS;   // row R + 3
     // (1) rows R .. R+3 of tile row TR -> shared vectors (held by the lanes with gr >> 2 == D & 1)
-    if ((gr >> 2) == (D & 1)) static_store_rows<MT, SR, TR, TR>(c, sm, scratch + (gr & 3) * VS + 2 * tg);
+    if ((gr >> 2) == (D & 1))
+      static_store_rows<MT, SR, TR, TR>(c, sm, scratch + (((gr & 1) << 1) | ((gr >> 1) & 1)) * VS + 2 * tg);
     __syncwarp();
     const double piv1 = u[R + 1];
     if (!static_pivot_ok<T::M, BOUNDED>(piv1, u, R + 1)) return R;
@@ -327,7 +331,7 @@ __device__ __forceinline__ int warp_pfaffian_static_steps(double (&c)[Tiles<MT>:
     {
       const double t2 = u[R + 2] * inv1, t3 = u[R + 3] * inv1, w2 = v[R + 2], w3 = v[R + 3];
 #pragma unroll
-      for (int q = 0; q < (T::M + 31) / 32; ++q) {
+      for (int q = (R + 2) / 32; q < (T::M + 31) / 32; ++q) {  // entries below R + 2 are dead
         const int cc = lane + 32 * q;
         if (cc >= R + 2 && cc < T::M) {
           const double tc = u[cc] * inv1, wc = v[cc];
@@ -361,8 +365,9 @@ __device__ __forceinline__ int warp_pfaffian_static_steps(double (&c)[Tiles<MT>:
     // (3) fragments: lane tg reads vector {w, u, w', u'}[tg] for A and {u, w, u', w'}[tg] for B
     const double sa = odd ? ((tg & 2) ? -inv2 : -inv1) : 1.0;
     const double sb = odd ? 1.0 : ((tg & 2) ? inv2 : inv1);
-    const double* srcA = scratch + (tg ^ 1) * VS + gr;
-    const double* srcB = scratch + tg * VS + gr;
+    const int ka = tg ^ 1;
+    const double* srcA = scratch + (((ka & 1) << 1) | (ka >> 1)) * VS + gr;
+    const double* srcB = scratch + (((tg & 1) << 1) | (tg >> 1)) * VS + gr;
 #pragma unroll
     for (int t = TR; t < MT; ++t) {
       af[t] = sa * srcA[8 * t];
