@@ -13,46 +13,109 @@
 
 namespace mcb200 {
 
+// Rotation gate on nk columns cc = first + step * j, visited in the rotated order j = rot, rot + 1, ... (mod nk): two
+// Givens pairs (i1, j1), (i2, j2) of the 4-row block; the pair layout is the only thing that depends on the kind
+// (RXRX (0,3)(1,2), RYRY (0,2)(1,3), RZRZ (0,1)(2,3)).  The rotation staggers the columns touched by neighbouring
+// gates at the same time, which is what keeps lane = gate accesses off the same shared-memory banks.
+template <bool UNIT>
+__device__ __forceinline__ void apply_rotation_columns(int kind, int wire0, double2 a, double2 b, double* X, int ld,
+                                                       int first, int step, int nk, int rot) {
+  const int j1 = 3 - kind, i2 = (kind == MCB200_GATE_RZRZ) ? 2 : 1, j2 = (kind == MCB200_GATE_RXRX) ? 2 : 3;
+  double* x0 = X + (2 * wire0) * ld + first;
+  double* x1 = x0 + j1 * ld;
+  double* x2 = x0 + i2 * ld;
+  double* x3 = x0 + j2 * ld;
+  int j = rot;
+#pragma unroll 4
+  for (int k = 0; k < nk; ++k) {
+    const int cc = UNIT ? j : j * step;
+    const double p = x0[cc], q = x1[cc], r = x2[cc], t = x3[cc];
+    x0[cc] = a.x * p + a.y * q;
+    x1[cc] = a.x * q - a.y * p;
+    x2[cc] = b.x * r + b.y * t;
+    x3[cc] = b.x * t - b.y * r;
+    if (++j == nk) j = 0;
+  }
+}
+
 // Build X = R[:, cols[c0 .. c0+mc)] in shared memory (d x mc, leading dimension ld).  coef holds the rotation
 // coefficients (4 doubles per gate) of up to coef_cap gates: whole layers are batched so that the sincos phase keeps
-// every thread busy and costs one barrier per batch instead of one per layer.  All threads of the block participate.
+// every thread busy and costs one block barrier per batch.  Columns never mix, so every WARP owns a fixed subset of
+// the columns (cc = warp, warp + n_warps, ...) and walks the layers on its own: a layer boundary is a __syncwarp, not
+// a block barrier.  Inside a warp the lanes are spread over (gate, column sub-group) items.  All threads participate.
 __device__ void build_columns(const CircuitDev& c, const double* prow, const int32_t* cols, int c0, int mc,
                               double* X, int ld, double* coef, int coef_cap) {
   const int d = 2 * c.n_qubits;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, w = tid >> 5, nw = nthr >> 5;
   const int shift = ((mc & (mc - 1)) == 0) ? (31 - __clz(mc)) : -1;  // mc power of two: index split by shift
   for (int idx = tid; idx < d * mc; idx += nthr) {
     int r = shift >= 0 ? (idx >> shift) : idx / mc, cc = idx - r * mc;
     int col = cols ? cols[c0 + cc] : c0 + cc;
     X[r * ld + cc] = (r == col) ? 1.0 : 0.0;
   }
-  __syncthreads();
+  // warp w owns the contiguous columns [base, base + wc)
+  const int cpw = (mc + nw - 1) / nw;
+  const int base = w * cpw;
+  const int wc = min(cpw, mc - base);  // <= 0: none
   int l = c.n_layers - 1;
   while (l >= 0) {
     const int ge = c.layer_ptr[l + 1];
     int lb = l;
     while (lb > 0 && ge - c.layer_ptr[lb - 1] <= coef_cap) --lb;
     const int gb = c.layer_ptr[lb];
+    __syncthreads();  // X initialised / every warp is done with the previous batch's coefficients
+    // coefficients of the batch, structure of arrays: (c1, t1) of gate k at coefA[k], (c2, t2) at coefB[k]
+    double2* coefA = reinterpret_cast<double2*>(coef);
+    double2* coefB = coefA + coef_cap;
     for (int g = gb + tid; g < ge; g += nthr) {
       const mcb200_gate_t gt = c.gates[g];
-      if (gt.kind <= MCB200_GATE_RZRZ) gate_coefficients(c, gt, prow, coef + 4 * (g - gb));
+      if (gt.kind <= MCB200_GATE_RZRZ) {
+        double cf[4];
+        gate_coefficients(c, gt, prow, cf);
+        coefA[g - gb] = make_double2(cf[0], cf[1]);
+        coefB[g - gb] = make_double2(cf[2], cf[3]);
+      }
     }
     __syncthreads();
-    // a work item = (gate, column group): the gate record and its coefficients are read once and reused for
-    // every column of the group (columns cc = group, group + CG, ...)
-    const int CG = mc >= 4 ? 4 : mc;
-    for (int ll = l; ll >= lb; --ll) {
-      const int g0 = c.layer_ptr[ll], ng = c.layer_ptr[ll + 1] - g0;
-      for (int it = tid; it < ng * CG; it += nthr) {
-        const int g = (CG == 4) ? (it >> 2) : it / CG, grp = it - g * CG;
-        const mcb200_gate_t gt = c.gates[g0 + g];
-        const double* cf = coef + 4 * (g0 + g - gb);
-        apply_gate_columns(c, gt, cf, prow, X, ld, grp, CG, mc);
+    if (wc > 0) {
+      const bool wc_pow2 = (wc & (wc - 1)) == 0;
+      for (int ll = l; ll >= lb; --ll) {
+        const int g0 = c.layer_ptr[ll], ng = c.layer_ptr[ll + 1] - g0;
+        if (ng > 16 || wc == 1) {
+          // lane = gate, all of the warp's columns; neighbouring gates start at staggered columns (bank spread)
+          for (int g = lane; g < ng; g += 32) {
+            const mcb200_gate_t gt = c.gates[g0 + g];
+            if (gt.kind <= MCB200_GATE_RZRZ) {
+              const int k = g0 + g - gb;
+              apply_rotation_columns<true>(gt.kind, gt.wire0, coefA[k], coefB[k], X, ld, base, 1, wc,
+                                           wc_pow2 ? ((g >> 2) & (wc - 1)) : 0);
+            } else {
+              apply_gate_columns(c, gt, nullptr, prow, X, ld, base, 1, base + wc);
+            }
+          }
+        } else {
+          // few gates per layer: S column sub-groups per gate so that ng * S items keep the lanes busy
+          int S = ng > 8 ? 2 : (ng > 4 ? 4 : 8);
+          if (S > wc) S = wc;
+          for (int it = lane; it < ng * S; it += 32) {
+            const int g = it / S, sub = it - g * S;
+            const mcb200_gate_t gt = c.gates[g0 + g];
+            if (gt.kind <= MCB200_GATE_RZRZ) {
+              const int k = g0 + g - gb;
+              apply_rotation_columns<false>(gt.kind, gt.wire0, coefA[k], coefB[k], X, ld, base + sub, S,
+                                            (wc - sub + S - 1) / S, 0);
+            } else {
+              apply_gate_columns(c, gt, nullptr, prow, X, ld, base + sub, S, base + wc);
+            }
+          }
+        }
+        __syncwarp();
       }
-      __syncthreads();
     }
     l = lb - 1;
   }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------- kernels

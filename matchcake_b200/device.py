@@ -143,6 +143,7 @@ class NonInteractingFermionicDevice:
         self.output_device = kwargs.get("output_device", "cpu")
         self.show_progress = kwargs.get("show_progress", False)
         self.apply_metadata: defaultdict = defaultdict()
+        self._bits_cache: dict = {}
         self._circuit_cache: "OrderedDict[tuple, _ops.CompiledCircuit]" = OrderedDict()
         self._group_cache: dict = {}
         self._plan_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
@@ -551,6 +552,17 @@ class NonInteractingFermionicDevice:
     def get_state_probability(self, target_binary_state, wires=None):
         return self.get_states_probability(target_binary_state, wires)
 
+    def _bits_device(self, bits: np.ndarray) -> torch.Tensor:
+        """Small 0/1 vectors (initial state, target outcome) as cached int8 device tensors: no per-call H2D copy."""
+        arr = np.ascontiguousarray(bits, dtype=np.int8)
+        key = (arr.shape, arr.tobytes())
+        t = self._bits_cache.get(key)
+        if t is None:
+            if len(self._bits_cache) > 256:
+                self._bits_cache.clear()
+            t = self._bits_cache[key] = torch.as_tensor(arr, device=self.torch_device)
+        return t
+
     def _probs_device(self, target: np.ndarray, wire_idx: np.ndarray) -> torch.Tensor:
         """(B, Q) probabilities for outcomes ``target`` (Q, k) measured on shared wire indices (k,)."""
         n = self.num_wires
@@ -559,8 +571,8 @@ class NonInteractingFermionicDevice:
         full_register = k == n and np.array_equal(wire_idx, np.arange(n))
         if (full_register and target.shape[0] == 1 and self._is_basis_input() and len(segments) == 1
                 and segments[0][0] == "gates" and n <= self.FUSED_MAX_QUBITS):
-            bits = torch.as_tensor(self._state_prep_op.basis_state_bits().astype(np.int8), device=self.torch_device)
-            tgt = torch.as_tensor(target[0].astype(np.int8), device=self.torch_device)
+            bits = self._bits_device(self._state_prep_op.basis_state_bits())
+            tgt = self._bits_device(target[0])
             return _ops.circuit_expval_projector(segments[0][1], segments[0][2], bits, tgt)[:, None]
         maj = np.stack([2 * wire_idx, 2 * wire_idx + 1], axis=1).ravel()
         cov = self._cov_device(maj)
@@ -587,9 +599,13 @@ class NonInteractingFermionicDevice:
                 f"The target binary state must have {w.shape[-1]} elements. Got {len(target)} instead.")
             target = target[None]
         if w.ndim == 1:
-            w = np.broadcast_to(w, target.shape)
-        widx = np.vectorize(self._wire_index, otypes=[int])(w) if w.size else np.zeros(w.shape, dtype=int)
-        same = len(target) <= 1 or bool(np.all(widx == widx[0]))
+            # one shared wire list: map it once (the common case of a single projector / qml.probs)
+            row = np.fromiter((self._wire_index(x) for x in w), dtype=int, count=len(w))
+            widx = np.broadcast_to(row, target.shape)
+            same = True
+        else:
+            widx = np.vectorize(self._wire_index, otypes=[int])(w) if w.size else np.zeros(w.shape, dtype=int)
+            same = len(target) <= 1 or bool(np.all(widx == widx[0]))
         if same:
             p = self._probs_device(target, widx[0])  # (B, Q)
         else:

@@ -50,7 +50,8 @@ def _as_f64_tensor(x, device=None, keep_grad: bool = False) -> torch.Tensor:
         t = torch.as_tensor(np.ascontiguousarray(a.real if np.iscomplexobj(a) else a))
     t = t.to(torch.float64)
     if device is not None:
-        t = t.to(device)
+        # pinned host memory: asynchronous copy on the current stream (the kernels that consume it run on that stream)
+        t = t.to(device, non_blocking=t.device.type == "cpu" and t.is_pinned())
     return t
 
 
