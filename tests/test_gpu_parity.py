@@ -285,6 +285,35 @@ def test_sector_features_random_pauli_sums(n, terms):
     np.testing.assert_allclose(total.cpu().numpy(), ref, rtol=RTOL, atol=1e-12)
 
 
+@pytest.mark.parametrize("m", [4, 8, 12, 16, 24, 32, 40, 48, 64])
+def test_pfaffian_static_path_hand_over(m):
+    """The tile Pfaffian eliminates pairs (2s, 2s+1) in place while the natural pivot passes its guard and hands the
+    remaining Schur complement to the pivoted routine otherwise: force the hand-over at every possible pair (zero and
+    tiny natural pivots, first and second pair of a double step) and compare with the oracle's signed Pfaffian."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(m)
+    mats = []
+    for s in range(m // 2):
+        for eps in (0.0, 1e-9):
+            a = random_skew(rng, (m, m))
+            a[2 * s, 2 * s + 1], a[2 * s + 1, 2 * s] = eps, -eps
+            mats.append(a)
+    # pivots that vanish only AFTER earlier eliminations (the natural pivot of the Schur complement is zero)
+    for s in range(1, m // 2):
+        a = random_skew(rng, (m, m))
+        lead = a[:2 * s, :2 * s]
+        b12 = a[:2 * s, 2 * s:2 * s + 2]
+        corr = (b12.T @ np.linalg.inv(lead) @ b12)[0, 1]   # Schur complement entry = a[2s][2s+1] + corr
+        a[2 * s, 2 * s + 1] = -corr
+        a[2 * s + 1, 2 * s] = corr
+        mats.append(a)
+    a_np = np.stack(mats)
+    ref = pfaffian.pfaffian_signed(a_np)
+    out = mops.pfaffian(dev(a_np), signed=True).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
+
+
 @pytest.mark.parametrize("n,terms,B", [(5, 40, 4), (9, 200, 3), (4, 300, 70)])
 def test_pauli_sum_small_fused_matches_oracle(n, terms, B):
     """Mixed-size sectors (0, 2, 4, 6) in ONE launch; longer Majorana strings accumulate through the sector path."""
