@@ -268,8 +268,11 @@ def main():
         def step(i):
             return kern(x_dev)
 
+        out_host = torch.empty((ns, ns), dtype=torch.float64).pin_memory()
+
         def e2e_step(i):
-            return kern(x_host).cpu()
+            out_host.copy_(kern(x_host))  # host features in, Gram read back into (pinned) host memory
+            return out_host
 
         entries = ns * (ns - 1) // 2
         units_per_step = entries
@@ -330,15 +333,27 @@ def main():
             cov = mops.cov_basis(xcols, n)
             return mops.probs_all(cov, normalize=True)
 
-        e2e_step = None
+        # end to end through the device API: one op object per gate (2016), parameters from pinned host memory
+        from matchcake_b200.operations import SptmCompRxRx, SptmCompRyRy, SptmCompRzRz
+        op_cls = (SptmCompRxRx, SptmCompRyRy, SptmCompRzRz)
+        host_params = params.cpu().pin_memory()
+        qdev = mc.NonInteractingFermionicDevice(wires=n, output_device="cpu")
+        layout = [(op_cls[l % 3], w) for l in range(depth) for w in range(l % 2, n - 1, 2)]
+
+        def e2e_step(i):
+            p = host_params.to(dev, non_blocking=True).view(B, len(layout), 2)
+            ops_ = [cls(p[:, j], wires=[w, w + 1]) for j, (cls, w) in enumerate(layout)]
+            qdev.execute_generator(ops_, reset=True)
+            return qdev.analytic_probability(list(range(k)))
+
         units_per_step = B * ws
-        e2e_units = 0
+        e2e_units = B * ws
         metric, unit, scaling = "marginal_distributions_per_sec", "distributions/s", "weak"
         cfg = {"workload": WORKLOADS["c4"], "n_qubits": n, "batch_per_gpu": B, "l2": "parameter tensor 528 MB > 126 MiB L2"}
         kernel_name = "circuit_columns_kernel"
         alg_flops_per_launch = len(gates) * 12 * (2 * k) * B
         launches_per_step = None
-        h2d, d2h = 0, 0
+        h2d, d2h = B * off * 8, B * (2 ** k) * 8
 
     # ------------------------------------------------------------------ device-resident timing
     for i in range(W):
