@@ -329,8 +329,8 @@ extern "C" int mcb200_cov_basis(const double* X, const int8_t* bits, int64_t B, 
   if (X == nullptr || cov_out == nullptr) return set_error("cov_basis: NULL pointer");
   const int d = 2 * n_qubits;
   const size_t smem = ((size_t)d * m + (size_t)m * (m + 1)) * sizeof(double);
-  if (smem > (size_t)kMaxDynSmem)
-    return set_error("cov_basis: d=%d m=%d needs %zu B of shared memory; use mcb200_cov_dense", d, m, smem);
+  // wide panels: one DMMA GEMM (P = E^T diag(s) O) + antisymmetrisation; the shared-memory kernel serves the narrow ones
+  if (m > 64 || smem > 96 * 1024) return cov_basis_gemm(X, bits, B, n_qubits, m, cov_out, as_stream(stream));
   if (int rc = check_cuda(cudaFuncSetAttribute(cov_basis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)smem), "cudaFuncSetAttribute(cov_basis)"))
     return rc;

@@ -8,6 +8,7 @@
 // Shared-memory leading dimensions are chosen so that the 8-byte fragment reads of a half-warp hit 16
 // distinct bank pairs (ld = 4 mod 16).
 #include "common.cuh"
+#include "tiles_api.cuh"
 
 namespace mcb200 {
 
@@ -29,6 +30,9 @@ struct GemmArgs {
   int M, N, K;
   int lda, ldb, ldc;
   long long batch;
+  // optional sign per K index applied to op(A): -1, or +1 where kbits[k] != 0 (basis-state Lambda_0, cov_basis_gemm)
+  int use_ksign = 0;
+  const int8_t* kbits = nullptr;
 };
 
 template <bool TA, bool TB>
@@ -60,6 +64,7 @@ __global__ void __launch_bounds__(256) bgemm_dmma_kernel(GemmArgs g) {
       if (!TA) { mm = e / BK; kk = e % BK; } else { kk = e / BM; mm = e % BM; }
       int gm = m0 + mm, gk = k0 + kk;
       ra[t] = (gm < g.M && gk < g.K) ? (TA ? A[(long long)gk * g.lda + gm] : A[(long long)gm * g.lda + gk]) : 0.0;
+      if (g.use_ksign && gk < g.K && !(g.kbits != nullptr && g.kbits[gk])) ra[t] = -ra[t];
       // B tile element (kk, nn)
       int nn;
       if (!TB) { kk = e / BN; nn = e % BN; } else { nn = e / BK; kk = e % BK; }
@@ -285,6 +290,47 @@ __global__ void gather_columns_kernel(const double* R, long long sR, int d, int 
     else v = (row == col) ? 1.0 : 0.0;
     x[e] = v;
   }
+}
+
+// cov <- cov - cov^T in place (one thread per pair i < j; the diagonal becomes 0)
+__global__ void antisymmetrize_kernel(double* cov, long long B, int m) {
+  const long long pairs = (long long)m * (m + 1) / 2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < B * pairs;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / pairs;
+    long long t = e - b * pairs;
+    int i = 0;
+    while (t >= m - i) {  // row i holds m - i pairs (j = i .. m-1)
+      t -= m - i;
+      ++i;
+    }
+    const int j = i + (int)t;
+    double* c = cov + b * (long long)m * m;
+    if (i == j) {
+      c[i * m + i] = 0.0;
+    } else {
+      const double x = c[i * m + j], y = c[j * m + i];
+      c[i * m + j] = x - y;
+      c[j * m + i] = y - x;
+    }
+  }
+}
+
+// K2 for large panels: Lambda = X^T Lambda_0 X with the 2x2-block-diagonal Lambda_0 of a basis state is P - P^T,
+// P = E^T diag(s) O, E / O = even / odd rows of X (d x m, row stride 2m): one (m x N x m) DMMA GEMM, N = d / 2, instead
+// of the two (d x d x m) products of the dense formulation (nif_device.py:1118-1131).
+int cov_basis_gemm(const double* X, const int8_t* bits, long long B, int n_qubits, int m, double* cov_out,
+                   cudaStream_t st) {
+  const int d = 2 * n_qubits;
+  GemmArgs g{X, X + m, cov_out, (long long)d * m, (long long)d * m, (long long)m * m, m, m, n_qubits, 2 * m, 2 * m, m, B};
+  g.use_ksign = 1;
+  g.kbits = bits;
+  if (int rc = launch_bgemm(g, 1, 0, B, st)) return rc;
+  const long long work = B * ((long long)m * (m + 1) / 2);
+  long long blocks = (work + 255) / 256;
+  if (blocks > 64LL * kNumSMs) blocks = 64LL * kNumSMs;
+  antisymmetrize_kernel<<<(unsigned)blocks, 256, 0, st>>>(cov_out, B, m);
+  return check_launch("antisymmetrize_kernel");
 }
 
 }  // namespace mcb200

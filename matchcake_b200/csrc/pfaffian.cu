@@ -353,6 +353,7 @@ extern "C" int mcb200_pfaffian(const double* A, int64_t n, int32_t m, int32_t mo
   }
   if (A == nullptr) return set_error("pfaffian: A is NULL");
   if (m <= kTilesMaxM) return tiles_pfaffian_plain(A, n, m, mode, scale, out, st);
+  if (m <= kBlockTilesMaxM) return block_tiles_pfaffian_plain(A, n, m, mode, scale, out, st);
   PlainLoader ld{A, out, scale, mode};
   return launch_pfaffian(ld, n, m, (double*)workspace, st, "pfaffian_kernel");
 }
@@ -367,6 +368,8 @@ extern "C" int mcb200_probs(const double* cov, const int8_t* outcomes, int64_t B
   cudaStream_t st = as_stream(stream);
   if (2 * k <= kTilesMaxM) {
     if (int rc = tiles_pfaffian_probs(cov, outcomes, B, Q, k, out, st)) return rc;
+  } else if (2 * k <= kBlockTilesMaxM) {
+    if (int rc = block_tiles_pfaffian_probs(cov, outcomes, B, Q, k, out, st)) return rc;
   } else {
     ProbsLoader ld{cov, outcomes, out, Q, k};
     if (int rc = launch_pfaffian(ld, (long long)B * Q, 2 * k, nullptr, st, "probs_kernel")) return rc;
@@ -396,6 +399,7 @@ extern "C" int mcb200_sector_features(const double* cov, int64_t B, int32_t D, c
   }
   if (s > kWarpKernelMaxM) return set_error("sector_features: sector size %d > %d", s, kWarpKernelMaxM);
   if (s <= kTilesMaxM) return tiles_pfaffian_sector(cov, B, D, index_sets, T, s, feats, st);
+  if (s <= kBlockTilesMaxM) return block_tiles_pfaffian_sector(cov, B, D, index_sets, T, s, feats, st);
   SectorLoader ld{cov, index_sets, feats, D, T};
   return launch_pfaffian(ld, n, s, nullptr, st, "sector_pfaffian_kernel");
 }
@@ -446,6 +450,8 @@ extern "C" int mcb200_gram(const double* cov0, const double* cov1, int64_t n0, i
   GramArgs g{cov0, cov1, n0, n1, d, row_begin, mode, scale, K, ldk};
   if (d <= kTilesMaxM) {
     if (int rc = tiles_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st)) return rc;
+  } else if (d <= kBlockTilesMaxM) {
+    if (int rc = block_tiles_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, st)) return rc;
   } else if (d <= kWarpKernelMaxM) {
     const size_t per_warp = (size_t)d * (d + 1) * sizeof(double);
     int warps = (int)((200 * 1024) / per_warp);

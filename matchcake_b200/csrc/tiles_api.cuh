@@ -12,12 +12,25 @@ int tiles_pfaffian_probs(const double* cov, const int8_t* outcomes, long long B,
                          cudaStream_t st);
 int tiles_pfaffian_sector(const double* cov, long long B, int D, const int32_t* index_sets, int T, int s,
                           double* feats, cudaStream_t st);
+// 64 < m <= 128: block-per-matrix variant with the tiles in shared memory (pfaffian_block_tiles.cu)
+constexpr int kBlockTilesMaxM = 128;
+int block_tiles_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out,
+                               cudaStream_t st);
+int block_tiles_pfaffian_probs(const double* cov, const int8_t* outcomes, long long B, int Q, int k, double* out,
+                               cudaStream_t st);
+int block_tiles_pfaffian_sector(const double* cov, long long B, int D, const int32_t* index_sets, int T, int s,
+                                double* feats, cudaStream_t st);
+int block_tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
+                     long long row_end, int mode, double scale, double* K, long long ldk, cudaStream_t st);
 long long tiles_gram_workspace_bytes(long long n0, long long n1, int d);
 int tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
                long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,
                cudaStream_t st);
 // every outcome of k measured wires at once (outcome index MSB first); returns -1 if k is too large for the tree kernel
 int tiles_probs_all(const double* cov, long long B, int k, int normalize, double* out, cudaStream_t st);
+// K2 as one DMMA GEMM + antisymmetrisation (gemm.cu), for panels too large for the shared-memory kernel
+int cov_basis_gemm(const double* X, const int8_t* bits, long long B, int n_qubits, int m, double* cov_out,
+                   cudaStream_t st);
 int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long long B, const int8_t* init_bits,
                        const int8_t* target_bits, double* out, cudaStream_t st);
 }  // namespace mcb200

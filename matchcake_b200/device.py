@@ -92,7 +92,7 @@ class NonInteractingFermionicDevice:
     C_DTYPE = torch.complex128
     DEFAULT_PROB_STRATEGY = "LookupTable"
     DEFAULT_CONTRACTION_METHOD = "neighbours"
-    FUSED_MAX_QUBITS = 59  # shared-memory limit of the fused projector kernel
+    FUSED_MAX_QUBITS = 32  # 2N <= 64: warp-per-instance fused kernel; larger registers take K1 -> K2 -> K3 (block-tile Pfaffian)
     FUSED_SECTOR_MAX = 6   # Majorana strings up to this length take the fused Pauli-sum kernel
 
     @staticmethod

@@ -285,7 +285,7 @@ def test_sector_features_random_pauli_sums(n, terms):
     np.testing.assert_allclose(total.cpu().numpy(), ref, rtol=RTOL, atol=1e-12)
 
 
-@pytest.mark.parametrize("m", [4, 8, 12, 16, 24, 32, 40, 48, 64])
+@pytest.mark.parametrize("m", [4, 8, 12, 16, 24, 32, 40, 48, 64, 66, 80, 100, 128])
 def test_pfaffian_static_path_hand_over(m):
     """The tile Pfaffian eliminates pairs (2s, 2s+1) in place while the natural pivot passes its guard and hands the
     remaining Schur complement to the pivoted routine otherwise: force the hand-over at every possible pair (zero and
@@ -373,7 +373,7 @@ def test_sptm_matmul(n, batch, ta, tb):
 
 
 # ------------------------------------------------------------------ Gram
-@pytest.mark.parametrize("n,shape", [(4, (13, 13)), (4, (9, 14)), (4, (14, 9)), (16, (10, 10)), (32, (6, 6)), (70, (3, 4))])
+@pytest.mark.parametrize("n,shape", [(4, (13, 13)), (4, (9, 14)), (4, (14, 9)), (16, (10, 10)), (32, (6, 6)), (40, (5, 6)), (64, (4, 4)), (70, (3, 4))])
 def test_gram_matches_reference_formulation(n, shape):
     from matchcake_b200 import ops as mops
 
