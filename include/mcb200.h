@@ -65,6 +65,10 @@ typedef struct mcb200_circuit {
   const double* scale;          /* device, P or NULL                                                 */
   const double* bias;           /* device, P or NULL                                                 */
   const double* consts;         /* device or NULL                                                    */
+  int32_t nearest_neighbour;    /* 1: EVERY gate (fSWAPs included) acts on adjacent wires, wire1 == wire0 + 1 --
+                                 * enables the register-resident chain kernel (<= 64 qubits, narrow panels);
+                                 * 0: unknown / general                                               */
+  int32_t reserved;
 } mcb200_circuit_t;
 
 /* ------------------------------------------------------------------ library */

@@ -31,7 +31,8 @@ class GateStruct(C.Structure):
 
 class CircuitStruct(C.Structure):
     _fields_ = [("gates", c_vp), ("layer_ptr", c_vp), ("n_gates", c_i32), ("n_layers", c_i32),
-                ("n_qubits", c_i32), ("n_param_cols", c_i32), ("scale", c_vp), ("bias", c_vp), ("consts", c_vp)]
+                ("n_qubits", c_i32), ("n_param_cols", c_i32), ("scale", c_vp), ("bias", c_vp), ("consts", c_vp),
+                ("nearest_neighbour", c_i32), ("reserved", c_i32)]
 
 
 # name -> (restype, argtypes); every symbol include/mcb200.h declares

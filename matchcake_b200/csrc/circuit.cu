@@ -299,6 +299,12 @@ extern "C" int mcb200_circuit_columns(const mcb200_circuit_t* circuit_host, cons
   if (X_out == nullptr) return set_error("X_out is NULL");
   if (c.n_param_cols > 0 && params == nullptr) return set_error("params is NULL");
   const int d = 2 * c.n_qubits;
+  // narrow panels (marginals over <= 4 wires) of nearest-neighbour circuits: register-resident kernel; wider panels
+  // stay on the shared-memory kernel, which shares the trigonometry between the columns (see circuit_brick.cu)
+  if (c.nearest_neighbour && c.n_qubits <= 64 && m <= 8 && c.n_gates > 0) {
+    const int rc = circuit_columns_brick_launch(c, params, B, cols, m, X_out, as_stream(stream));
+    if (rc >= 0) return rc;
+  }
   // coefficient buffer: at least one full layer (<= N gates on disjoint wires), normally 256 gates per batch
   const int max_layer_gates = c.n_qubits > 256 ? c.n_qubits : 256;
   // column chunk so that X (d x mc) + coefficients fit in shared memory

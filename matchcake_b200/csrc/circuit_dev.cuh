@@ -12,6 +12,7 @@ struct CircuitDev {
   const double* scale;
   const double* bias;
   const double* consts;
+  int nearest_neighbour;
 };
 
 // Coefficients of one rotation gate for one circuit instance: {c1, t1, c2, t2} (two independent Givens pairs).
@@ -143,6 +144,7 @@ static inline int circuit_to_dev(const mcb200_circuit_t* h, mcb200::CircuitDev* 
   c->scale = h->scale;
   c->bias = h->bias;
   c->consts = h->consts;
+  c->nearest_neighbour = h->nearest_neighbour;
   return 0;
 }
 

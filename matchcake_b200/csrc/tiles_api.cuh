@@ -31,6 +31,10 @@ int tiles_probs_all(const double* cov, long long B, int k, int normalize, double
 // K2 as one DMMA GEMM + antisymmetrisation (gemm.cu), for panels too large for the shared-memory kernel
 int cov_basis_gemm(const double* X, const int8_t* bits, long long B, int n_qubits, int m, double* cov_out,
                    cudaStream_t st);
+// K1 with the panel in registers (circuit_brick.cu): nearest-neighbour circuits, <= 64 qubits; -1 = not applicable
+struct CircuitDev;
+int circuit_columns_brick_launch(const CircuitDev& c, const double* params, long long B, const int32_t* cols, int m,
+                                 double* X_out, cudaStream_t st);
 int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long long B, const int8_t* init_bits,
                        const int8_t* target_bits, double* out, cudaStream_t st);
 }  // namespace mcb200

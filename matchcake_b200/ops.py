@@ -114,7 +114,8 @@ class CompiledCircuit:
         self._struct = CircuitStruct(
             gates=_ptr(self.gates_dev) if len(flat) else None, layer_ptr=_ptr(self.layer_ptr_dev),
             n_gates=len(flat), n_layers=len(ptr) - 1, n_qubits=self.n_qubits, n_param_cols=self.n_param_cols,
-            scale=_ptr(self.scale_dev), bias=_ptr(self.bias_dev), consts=_ptr(self.consts_dev))
+            scale=_ptr(self.scale_dev), bias=_ptr(self.bias_dev), consts=_ptr(self.consts_dev),
+            nearest_neighbour=int(all(g.wire1 == g.wire0 + 1 for g in flat)), reserved=0)
 
     @property
     def d(self) -> int:

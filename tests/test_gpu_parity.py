@@ -124,6 +124,41 @@ def test_circuit_sptm_general_gates():
     np.testing.assert_array_equal(out, np.broadcast_to(np.eye(6), (2, 6, 6)))
 
 
+@pytest.mark.parametrize("n", [2, 5, 16, 33, 64])
+@pytest.mark.parametrize("m", [1, 3, 8])
+def test_register_resident_chain_matches_general_kernel(n, m):
+    """Nearest-neighbour circuits, narrow panels: the register-resident kernel (circuit_brick.cu) against the oracle and,
+    bit for bit, against the shared-memory kernel (same arithmetic, different data movement)."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(100 * n + m)
+    B = 3
+    blk = gates.random_sptm(2, seed=n)
+    blk_b = gates.random_sptm(2, seed=n + 1, batch_size=B)
+    kinds = ["SptmCompRxRx", "SptmCompRyRy", "SptmCompRzRz"]
+    ops = []
+    for layer in range(7):
+        for w in range(layer % 2, n - 1, 2):
+            pick = (layer + w) % 6
+            if pick < 3:
+                ops.append(Op(kinds[pick], (w, w + 1), params=rng.uniform(0, 6, (B, 2))))
+            elif pick == 3:
+                ops.append(Op("SptmFSwap", (w, w + 1)))
+            elif pick == 4:
+                ops.append(Op("Sptm", (w, w + 1), matrix=blk))
+            else:
+                ops.append(Op("Sptm", (w, w + 1), matrix=blk_b))
+    circ, params = compiled(ops, n, B)
+    assert circ._struct.nearest_neighbour == 1
+    cols = torch.as_tensor(rng.permutation(2 * n)[:m].astype(np.int32))
+    ref = gates.chain(ops, n, contraction=None)[:, :, cols.numpy()]
+    fast = mops.circuit_columns(circ, params, cols).cpu().numpy()
+    np.testing.assert_allclose(fast, ref, rtol=RTOL, atol=ATOL)
+    circ._struct.nearest_neighbour = 0
+    general = mops.circuit_columns(circ, params, cols).cpu().numpy()
+    np.testing.assert_array_equal(fast, general)
+
+
 @pytest.mark.parametrize("n,n_features", [(4, 4), (6, 12), (32, 64), (128, 128)])
 def test_kernel_ansatz_sptm(n, n_features):
     """FermionicPQCKernel ansatz (affine map folded into the kernel) vs the oracle's _x_to_sptm."""
