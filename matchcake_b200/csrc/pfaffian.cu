@@ -1,9 +1,10 @@
-// K3: batched Pfaffians (plain, projector/probs read-out, Pauli-sector gather, Gram pairs).
-//
-// v1 layout: one warp per matrix, the matrix lives in that warp's slice of shared memory (strict upper
-// triangle only), Parlett-Reid elimination from pfaffian_dev.cuh.  Matrices larger than 128 x 128 use one
-// thread block per matrix with the working copy in a caller-provided global workspace (L2 resident).
-// "Loaders" form the matrix on the fly so that sums / gathers never round-trip through HBM:
+// K3: the C ABI of the batched Pfaffians (plain, projector / probs read-out, Pauli-sector gather, Gram pairs) and the
+// small kernels around them.  Dispatch by matrix size:
+//   m <= 64          register-tile kernels, one warp per matrix          (pfaffian_tiles.cu / .cuh)
+//   64 < m <= 128    shared-memory-tile kernels, one block per matrix    (pfaffian_block_tiles.cu)
+//   m > 128          scalar Parlett-Reid, one block per matrix, working copy in a caller-provided global workspace
+//                    (plain matrices and Gram cells only; pfaffian_dev.cuh)
+// Matrices are formed on the fly from their sources so that sums / gathers never round-trip through HBM:
 //   Plain   A[i]                              utils/_pfaffian.py:78-119
 //   Probs   cov[b] + Lambda_y(q)              product_state_strategy.py:196-213
 //   Sector  cov[b][S_t, S_t]                  utils/_pfaffian.py:39-75
@@ -32,64 +33,7 @@ struct PlainLoader {
   }
 };
 
-struct ProbsLoader {
-  const double* cov;       // (B, m, m)
-  const int8_t* outcomes;  // (Q, k)
-  double* out;             // (B, Q)
-  int Q, k;
-  __device__ void load(long long item, double* S, int lds, int m, int tid, int nthr) const {
-    long long b = item / Q;
-    int q = (int)(item - b * Q);
-    const double* src = cov + b * (long long)m * m;
-    const int8_t* y = outcomes + (long long)q * k;
-    for (int idx = tid; idx < m * m; idx += nthr) {
-      int i = idx / m, j = idx - i * m;
-      if (i < j) {
-        double v = src[idx];
-        if ((i & 1) == 0 && j == i + 1) v += y[i >> 1] ? 1.0 : -1.0;  // -(-1)^y
-        S[i * lds + j] = v;
-      }
-    }
-  }
-  __device__ void store(long long item, double pf) const { out[item] = ldexp(fabs(pf), -k); }
-};
-
-struct SectorLoader {
-  const double* cov;          // (B, D, D)
-  const int32_t* index_sets;  // (T, s)
-  double* feats;              // (B, T)
-  int D, T;
-  __device__ void load(long long item, double* S, int lds, int m, int tid, int nthr) const {
-    long long b = item / T;
-    int t = (int)(item - b * T);
-    const double* src = cov + b * (long long)D * D;
-    const int32_t* idx = index_sets + (long long)t * m;
-    for (int e = tid; e < m * m; e += nthr) {
-      int i = e / m, j = e - i * m;
-      if (i < j) S[i * lds + j] = src[(long long)idx[i] * D + idx[j]];
-    }
-  }
-  __device__ void store(long long item, double pf) const { feats[item] = pf; }
-};
-
 // ------------------------------------------------------------------------------------------- kernels
-template <class Loader, int kMaxChunks>
-__global__ void pfaffian_warp_kernel(Loader loader, long long n_items, int m) {
-  extern __shared__ double smem[];
-  const int lds = m + 1;
-  const int warps = blockDim.x >> 5;
-  double* S = smem + (size_t)warp_id() * m * lds;
-  const int lane = lane_id();
-  for (long long item = (long long)blockIdx.x * warps + warp_id(); item < n_items;
-       item += (long long)gridDim.x * warps) {
-    loader.load(item, S, lds, m, lane, 32);
-    __syncwarp();
-    double pf = warp_pfaffian_upper<kMaxChunks>(S, m, lds);
-    if (lane == 0) loader.store(item, pf);
-    __syncwarp();
-  }
-}
-
 template <class Loader>
 __global__ void pfaffian_block_global_kernel(Loader loader, long long n_items, int m, double* workspace) {
   __shared__ double red[8];
@@ -206,33 +150,13 @@ __global__ void enumerate_outcomes_kernel(int8_t* bits, int k) {
   bits[e] = (int8_t)((q >> (k - 1 - j)) & 1);
 }
 
-constexpr int kWarpKernelMaxM = 128;
+constexpr int kWarpKernelMaxM = kBlockTilesMaxM;  // largest matrix of the tile kernels
 constexpr int kBlockGlobalCtas = 4 * kNumSMs;
 
 template <class Loader>
 static int launch_pfaffian(const Loader& loader, long long n_items, int m, double* workspace, cudaStream_t st,
                            const char* what) {
   if (n_items == 0) return 0;
-  if (m <= kWarpKernelMaxM) {
-    const size_t per_warp = (size_t)m * (m + 1) * sizeof(double);
-    int warps = (int)((200 * 1024) / (per_warp ? per_warp : 1));
-    if (warps > 8) warps = 8;
-    if (warps < 1) warps = 1;
-    const size_t smem = per_warp * warps;
-    long long blocks = (n_items + warps - 1) / warps;
-    const long long cap = 64LL * kNumSMs;  // persistent-ish grid, multiple of the SM count
-    if (blocks > cap) blocks = cap;
-    auto launch = [&](auto kernel) -> int {
-      if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                              "cudaFuncSetAttribute(pfaffian_warp)"))
-        return rc;
-      kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(loader, n_items, m);
-      return check_launch(what);
-    };
-    if (m <= 32) return launch(pfaffian_warp_kernel<Loader, 1>);
-    if (m <= 64) return launch(pfaffian_warp_kernel<Loader, 2>);
-    return launch(pfaffian_warp_kernel<Loader, 4>);
-  }
   if (workspace == nullptr) return set_error("%s: m=%d needs a workspace (see *_workspace_bytes)", what, m);
   long long blocks = n_items < kBlockGlobalCtas ? n_items : kBlockGlobalCtas;
   pfaffian_block_global_kernel<Loader><<<(unsigned)blocks, 256, 0, st>>>(loader, n_items, m, workspace);
@@ -269,32 +193,6 @@ __device__ __forceinline__ bool gram_cell_active(const GramArgs& g, long long i,
 __device__ __forceinline__ void gram_store(const GramArgs& g, long long i, long long j, double v) {
   g.K[i * g.ldk + j] = v;
   if (g.mode == MCB200_GRAM_REFERENCE && j < g.n0 && i < g.n1) g.K[j * g.ldk + i] = v;  // gram_matrix.py:139-143
-}
-
-template <int kMaxChunks>
-__global__ void gram_warp_kernel(GramArgs g, long long rows, long long col_blocks) {
-  extern __shared__ double smem[];
-  const int m = g.d, lds = m + 1;
-  const int warps = blockDim.x >> 5;
-  double* S = smem + (size_t)warp_id() * m * lds;
-  const int lane = lane_id();
-  // flattened (row, column-block) index: gridDim.x can be huge, gridDim.y cannot
-  for (long long blk = blockIdx.x; blk < rows * col_blocks; blk += gridDim.x) {
-    const long long i = g.row_begin + blk / col_blocks;
-    const long long j = (blk % col_blocks) * warps + warp_id();
-    if (gram_cell_active(g, i, j)) {
-      const double* a = g.cov0 + i * (long long)m * m;
-      const double* b = g.cov1 + j * (long long)m * m;
-      for (int idx = lane; idx < m * m; idx += 32) {
-        int r = idx / m, c = idx - r * m;
-        if (r < c) S[r * lds + c] = a[idx] + b[idx];
-      }
-      __syncwarp();
-      double pf = warp_pfaffian_upper<kMaxChunks>(S, m, lds);
-      if (lane == 0) gram_store(g, i, j, g.scale * fabs(pf));
-      __syncwarp();
-    }
-  }
 }
 
 __global__ void gram_block_global_kernel(GramArgs g, long long rows, double* workspace) {
@@ -368,11 +266,8 @@ extern "C" int mcb200_probs(const double* cov, const int8_t* outcomes, int64_t B
   cudaStream_t st = as_stream(stream);
   if (2 * k <= kTilesMaxM) {
     if (int rc = tiles_pfaffian_probs(cov, outcomes, B, Q, k, out, st)) return rc;
-  } else if (2 * k <= kBlockTilesMaxM) {
-    if (int rc = block_tiles_pfaffian_probs(cov, outcomes, B, Q, k, out, st)) return rc;
   } else {
-    ProbsLoader ld{cov, outcomes, out, Q, k};
-    if (int rc = launch_pfaffian(ld, (long long)B * Q, 2 * k, nullptr, st, "probs_kernel")) return rc;
+    if (int rc = block_tiles_pfaffian_probs(cov, outcomes, B, Q, k, out, st)) return rc;
   }
   if (normalize) {
     normalize_rows_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(out, B, Q);
@@ -399,9 +294,7 @@ extern "C" int mcb200_sector_features(const double* cov, int64_t B, int32_t D, c
   }
   if (s > kWarpKernelMaxM) return set_error("sector_features: sector size %d > %d", s, kWarpKernelMaxM);
   if (s <= kTilesMaxM) return tiles_pfaffian_sector(cov, B, D, index_sets, T, s, feats, st);
-  if (s <= kBlockTilesMaxM) return block_tiles_pfaffian_sector(cov, B, D, index_sets, T, s, feats, st);
-  SectorLoader ld{cov, index_sets, feats, D, T};
-  return launch_pfaffian(ld, n, s, nullptr, st, "sector_pfaffian_kernel");
+  return block_tiles_pfaffian_sector(cov, B, D, index_sets, T, s, feats, st);
 }
 
 extern "C" int mcb200_rowdot(const double* feats, const double* coeffs, int64_t B, int32_t T, int32_t accumulate,
@@ -452,25 +345,6 @@ extern "C" int mcb200_gram(const double* cov0, const double* cov1, int64_t n0, i
     if (int rc = tiles_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st)) return rc;
   } else if (d <= kBlockTilesMaxM) {
     if (int rc = block_tiles_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, st)) return rc;
-  } else if (d <= kWarpKernelMaxM) {
-    const size_t per_warp = (size_t)d * (d + 1) * sizeof(double);
-    int warps = (int)((200 * 1024) / per_warp);
-    if (warps > 8) warps = 8;
-    if (warps < 1) warps = 1;
-    const size_t smem = per_warp * warps;
-    const long long col_blocks = (n1 + warps - 1) / warps;
-    long long blocks = rows * col_blocks;
-    const long long cap = 64LL * kNumSMs;
-    if (blocks > cap) blocks = cap;
-    auto launch = [&](auto kernel) -> int {
-      if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                              "cudaFuncSetAttribute(gram_warp)"))
-        return rc;
-      kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(g, rows, col_blocks);
-      return check_launch("gram_warp_kernel");
-    };
-    int rc = d <= 32 ? launch(gram_warp_kernel<1>) : d <= 64 ? launch(gram_warp_kernel<2>) : launch(gram_warp_kernel<4>);
-    if (rc) return rc;
   } else {
     if (workspace == nullptr) return set_error("gram: d=%d needs a workspace (mcb200_gram_workspace_bytes)", d);
     long long blocks = rows * n1 < kBlockGlobalCtas ? rows * n1 : kBlockGlobalCtas;

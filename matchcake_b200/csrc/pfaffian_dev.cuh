@@ -1,4 +1,6 @@
-// Device-side Parlett-Reid Pfaffian of a real skew-symmetric matrix held in shared memory.
+// Device-side scalar Parlett-Reid Pfaffian of a real skew-symmetric matrix held in shared or global memory (one
+// thread block per matrix): the path for matrices larger than the tile kernels take (m > 128) and for the
+// block-per-instance fused projector kernel.
 // Only the strict upper triangle A[i][j], i < j, is stored, read and updated (skew symmetry supplies the
 // rest), so the arithmetic is the ~m^3/3 flop of the structured algorithm, not the 2m^3/3 of a full update.
 //
@@ -30,71 +32,6 @@ __device__ __forceinline__ void skew_swap_item(double* A, int ld, int a, int b, 
   } else if (t == b) {
     A[a * ld + b] = -A[a * ld + b];
   }
-}
-
-// One warp, matrix private to the warp.  kMaxChunks >= ceil(m / 32).  Returns the signed Pfaffian in all lanes.
-template <int kMaxChunks>
-__device__ double warp_pfaffian_upper(double* A, int m, int ld) {
-  const int lane = lane_id();
-  if (m == 0) return 1.0;
-  if (m & 1) return 0.0;
-  double pf = 1.0;
-  for (int k = 0; k + 1 < m; k += 2) {
-    double best = -1.0;
-    int bj = m;
-    for (int j = k + 1 + lane; j < m; j += 32) {
-      double a = fabs(A[k * ld + j]);
-      if (a > best) {
-        best = a;
-        bj = j;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double oa = __shfl_xor_sync(0xffffffffu, best, o);
-      int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-      if (oa > best || (oa == best && oj < bj)) {
-        best = oa;
-        bj = oj;
-      }
-    }
-    if (!(best > 0.0)) return 0.0;  // exactly singular (or NaN): Pf = 0
-    if (bj != k + 1) {
-      for (int t = k + lane; t < m; t += 32) skew_swap_item(A, ld, k + 1, bj, t);
-      pf = -pf;
-      __syncwarp();
-    }
-    const double piv = A[k * ld + k + 1];
-    pf *= piv;
-    if (k + 2 >= m) break;
-    // registers: tau_j and w_j = A[k+1][j] for this lane's fixed columns j = lane + 32 c
-    double tau[kMaxChunks], w[kMaxChunks];
-#pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      int j = lane + 32 * c;
-      bool on = (j >= k + 2) && (j < m);
-      tau[c] = on ? A[k * ld + j] / piv : 0.0;
-      w[c] = on ? A[(k + 1) * ld + j] : 0.0;
-    }
-    // publish tau into row k so that tau_i can be read by every lane (broadcast)
-#pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      int j = lane + 32 * c;
-      if (j >= k + 2 && j < m) A[k * ld + j] = tau[c];
-    }
-    __syncwarp();
-    for (int i = k + 2; i < m - 1; ++i) {
-      const double ti = A[k * ld + i];
-      const double wi = A[(k + 1) * ld + i];
-#pragma unroll
-      for (int c = 0; c < kMaxChunks; ++c) {
-        int j = lane + 32 * c;
-        if (32 * c + 31 > i && j > i && j < m) A[i * ld + j] += wi * tau[c] - ti * w[c];
-      }
-    }
-    __syncwarp();
-  }
-  return pf;
 }
 
 // Whole thread block, matrix shared by the block.  `red` is shared scratch of >= 3 doubles + 2 ints (40 B).
