@@ -252,6 +252,47 @@ def test_two_wire_sptm_block_gradients():
     np.testing.assert_allclose(m.grad.cpu().numpy(), fd, rtol=2e-6, atol=2e-8)
 
 
+def test_dense_sptm_circuit_gradients_through_device():
+    """The reference's SPTM-circuit gradchecks (tests/test_devices/test_nif_device/test_gradients/
+    test_apply_mths_gradients.py:156-260): a dense SPTM with requires_grad behind a rotation gate, probabilities and a
+    Pauli-sum expectation value differentiated w.r.t. every matrix entry (covariance formulation, see the block test)."""
+    n, B = 3, 2
+    rng = np.random.default_rng(5)
+    r0 = gates.random_sptm(n, seed=3, batch_size=B)
+    p = rng.uniform(0, 6, (B, 2))
+    bits = np.array([1, 0, 1])
+    amp = cv.amplitudes_from_basis_state(bits)
+    wq = rng.standard_normal((B, 4))
+    states = readout.states_to_binary(np.arange(4), 2)
+    words, coeffs = ["ZII", "IZZ", "XXI", "IYY", "XZX"], rng.standard_normal(5)
+    wh = rng.standard_normal(B)
+
+    def chain_of(m):
+        return gates.chain([Op("SptmCompRxRx", (0, 1), params=p), Op("Sptm", (0, 1, 2), matrix=m)], n)
+
+    def f_probs(m):
+        pr = readout.probs_product_state(cv.evolve(cv.covariance_matrix(amp), chain_of(m)), states, np.array([0, 2])).T
+        return float((pr / pr.sum(axis=-1, keepdims=True) * wq).sum())
+
+    def f_expval(m):
+        return float((readout.expval_pauli_sum(cv.evolved_extended_covariance(amp, chain_of(m)), words, coeffs) * wh).sum())
+
+    for f, kind in ((f_probs, "probs"), (f_expval, "expval")):
+        fd = finite_difference(f, r0)
+        m = dev(r0, grad=True)
+        d = mc.NIFDevice(n)
+        d.execute_generator([BasisState(bits, wires=range(n)), SptmCompRxRx(dev(p), wires=[0, 1]),
+                             SingleParticleTransitionMatrixOperation(m, wires=range(n))], reset=True)
+        if kind == "probs":
+            out = d.analytic_probability([0, 2])
+            (out * dev(wq).to(out.device)).sum().backward()
+        else:
+            h = obs.Hamiltonian(list(coeffs), [obs.PauliWord({i: c for i, c in enumerate(w)}) for w in words])
+            out = d.expval(h)
+            (out * dev(wh).to(out.device)).sum().backward()
+        np.testing.assert_allclose(m.grad.cpu().numpy(), fd, rtol=2e-6, atol=2e-8)
+
+
 # ------------------------------------------------------------------ kernel alignment
 def test_kernel_alignment_gradient_and_ascent():
     from matchcake_b200.ml.kernels import FermionicPQCKernel
