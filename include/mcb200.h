@@ -258,6 +258,14 @@ int mcb200_sector_features_backward(const double* cov, int64_t B, int32_t D, con
 int mcb200_cov_basis_backward(const double* X, const int8_t* bits, int64_t B, int32_t n_qubits, int32_t m,
                               const double* grad_cov, double* grad_X, void* stream);
 
+/* Adjoint of mcb200_cov_dense with respect to R (L0 must be skew-symmetric, as every covariance is):
+ * grad_R[:, idx] = (L0 R~[:, idx]) (grad_cov^T - grad_cov) restricted to the rows of R; grad_R is (B, d, d), or (d, d)
+ * accumulated over the batch when strideR == 0.  Workspace as reported by the _workspace_bytes query. */
+int64_t mcb200_cov_dense_backward_workspace_bytes(int64_t B, int32_t D, int32_t m);
+int mcb200_cov_dense_backward(const double* R, int64_t strideR, const double* L0, int64_t strideL0, int64_t B,
+                              int32_t d, int32_t D, const int32_t* idx, int32_t m, const double* grad_cov,
+                              double* grad_R, void* workspace, void* stream);
+
 /* Adjoint of mcb200_circuit_columns.  X is the forward OUTPUT (B, 2N, m); the gates are un-applied in application
  * order, nothing has to be saved by the forward pass.  grad_angles (B, n_param_cols) is the derivative with respect
  * to the angle each gate actually used, i.e. AFTER the optional affine map bias + scale * x of the descriptor

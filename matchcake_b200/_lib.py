@@ -66,6 +66,8 @@ SIGNATURES = {
     "mcb200_probs_backward": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "mcb200_sector_features_backward": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "mcb200_cov_basis_backward": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "mcb200_cov_dense_backward_workspace_bytes": (c_i64, [c_i64, c_i32, c_i32]),
+    "mcb200_cov_dense_backward": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "mcb200_circuit_columns_backward": (c_i32, [C.POINTER(CircuitStruct), c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "mcb200_launch_count": (c_i64, []),
     "mcb200_reset_launch_count": (None, []),

@@ -74,6 +74,44 @@ class CovBasis(torch.autograd.Function):
         return gx, None, None
 
 
+class CovDense(torch.autograd.Function):
+    """cov = (R~^T L0 R~)[idx, idx] for product-state / extended covariances; adjoint w.r.t. R only (the initial-state
+    covariance is treated as a constant)."""
+
+    @staticmethod
+    def forward(ctx, r, l0, idx):
+        from . import ops
+        rd, ld = r.detach(), l0.detach()
+        ctx.idx = idx
+        ctx.r_shape = tuple(r.shape)
+        ctx.save_for_backward(rd, ld)
+        return ops.cov_dense(rd, ld, idx)
+
+    @staticmethod
+    def backward(ctx, gcov):
+        from . import ops
+        r, l0 = ctx.saved_tensors
+        r3 = r if r.ndim == 3 else r[None]
+        r3 = ops._f64(r3, "r")
+        l0 = ops._f64(l0, "l0")
+        Br, d, _ = r3.shape
+        D = l0.shape[-1]
+        gcov = gcov.to(torch.float64).contiguous()
+        B, m, _ = gcov.shape
+        sr = d * d if (Br == B and B > 1) else 0
+        sl = D * D if (l0.ndim == 3 and l0.shape[0] == B and B > 1) else 0
+        idx = None if ctx.idx is None else ctx.idx.to(device=r3.device, dtype=torch.int32).contiguous()
+        lib = _lib.load()
+        ws = torch.empty((lib.mcb200_cov_dense_backward_workspace_bytes(B, D, m) + 7) // 8, dtype=torch.float64,
+                         device=r3.device)
+        gr = torch.empty((B if sr else 1, d, d), dtype=torch.float64, device=r3.device)
+        check(lib.mcb200_cov_dense_backward(r3.data_ptr(), sr, l0.data_ptr(), sl, B, d, D,
+                                            None if idx is None else idx.data_ptr(), m, gcov.data_ptr(), gr.data_ptr(),
+                                            ws.data_ptr(), _stream()))
+        # a shared R (2-D, or batch of one) receives the sum over the batch: the kernel accumulates it when strideR == 0
+        return gr.reshape(ctx.r_shape), None, None
+
+
 class Pfaffian(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, signed, scale):

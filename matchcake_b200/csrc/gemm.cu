@@ -350,6 +350,76 @@ extern "C" int mcb200_sptm_matmul(const double* A, int64_t strideA, int transA, 
   return launch_bgemm(g, transA, transB, batch, as_stream(stream));
 }
 
+// Z[b] = G[b]^T - G[b]  (m x m)
+__global__ void transpose_minus_kernel(const double* __restrict__ G, long long B, int m, double* __restrict__ Z) {
+  const long long total = B * (long long)m * m;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / ((long long)m * m);
+    const int r = (int)((e - b * (long long)m * m) / m), c = (int)(e % m);
+    const double* g = G + b * (long long)m * m;
+    Z[e] = g[c * m + r] - g[r * m + c];
+  }
+}
+
+// grad_R[b][row][idx[c]] += Xbar[b][row][c] for row < d (the lifted row d of the extended covariance is constant)
+__global__ void scatter_columns_add_kernel(const double* __restrict__ Xbar, long long B, int d, int D, const int32_t* idx,
+                                           int m, double* grad_R, long long sR) {
+  const long long total = B * (long long)d * m;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / ((long long)d * m);
+    const int row = (int)((e - b * (long long)d * m) / m), c = (int)(e % m);
+    const int col = idx ? idx[c] : c;
+    if (col < d) atomicAdd(grad_R + b * sR + (long long)row * d + col, Xbar[b * (long long)D * m + (long long)row * m + c]);
+  }
+}
+
+extern "C" int64_t mcb200_cov_dense_backward_workspace_bytes(int64_t B, int32_t D, int32_t m) {
+  return (2 * B * (int64_t)D * m + B * (int64_t)m * m) * (int64_t)sizeof(double);
+}
+
+extern "C" int mcb200_cov_dense_backward(const double* R, int64_t strideR, const double* L0, int64_t strideL0, int64_t B,
+                                         int32_t d, int32_t D, const int32_t* idx, int32_t m, const double* grad_cov,
+                                         double* grad_R, void* workspace, void* stream) {
+  if (B < 0 || d < 1 || m < 0) return set_error("cov_dense_backward: bad sizes");
+  if (D != d && D != d + 1) return set_error("cov_dense_backward: D must be d or d+1 (got d=%d D=%d)", d, D);
+  if (B == 0) return 0;
+  if (grad_R == nullptr) return set_error("cov_dense_backward: grad_R is NULL");
+  cudaStream_t st = as_stream(stream);
+  const long long nR = (strideR == 0 ? 1 : B) * (long long)d * d;
+  if (int rc = check_cuda(cudaMemsetAsync(grad_R, 0, (size_t)nR * sizeof(double), st), "cudaMemsetAsync")) return rc;
+  if (m == 0) return 0;
+  if (R == nullptr || L0 == nullptr || grad_cov == nullptr || workspace == nullptr)
+    return set_error("cov_dense_backward: NULL pointer");
+  double* X = (double*)workspace;              // (B, D, m)   R~[:, idx], later Xbar
+  double* Y = X + B * (int64_t)D * m;          // (B, D, m)   L0 X
+  double* Z = Y + B * (int64_t)D * m;          // (B, m, m)   G^T - G
+  for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+    int64_t nb = B - b0 < 65535 ? B - b0 : 65535;
+    dim3 grid((unsigned)((D * m + 255) / 256 < 64 ? (D * m + 255) / 256 : 64), (unsigned)nb);
+    gather_columns_kernel<<<grid, 256, 0, st>>>(R + b0 * strideR, strideR, d, D, idx, m, X + b0 * (int64_t)D * m);
+    if (int rc = check_launch("gather_columns_kernel")) return rc;
+  }
+  GemmArgs g1{L0, X, Y, strideL0, (long long)D * m, (long long)D * m, D, m, D, D, m, m, B};
+  if (int rc = launch_bgemm(g1, 0, 0, B, st)) return rc;
+  {
+    const long long total = B * (long long)m * m;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 64LL * kNumSMs) blocks = 64LL * kNumSMs;
+    transpose_minus_kernel<<<(unsigned)blocks, 256, 0, st>>>(grad_cov, B, m, Z);
+    if (int rc = check_launch("transpose_minus_kernel")) return rc;
+  }
+  // Xbar = Y (G^T - G)   (L0 is skew: L0^T X = -Y)
+  GemmArgs g2{Y, Z, X, (long long)D * m, (long long)m * m, (long long)D * m, D, m, m, m, m, m, B};
+  if (int rc = launch_bgemm(g2, 0, 0, B, st)) return rc;
+  {
+    const long long total = B * (long long)d * m;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 64LL * kNumSMs) blocks = 64LL * kNumSMs;
+    scatter_columns_add_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, B, d, D, idx, m, grad_R, strideR);
+    return check_launch("scatter_columns_add_kernel");
+  }
+}
+
 extern "C" int64_t mcb200_cov_dense_workspace_bytes(int64_t B, int32_t D, int32_t m) {
   return 2 * B * (int64_t)D * m * (int64_t)sizeof(double);
 }

@@ -234,9 +234,10 @@ def cov_basis(x: torch.Tensor, n_qubits: int, bits: Optional[torch.Tensor] = Non
 
 def cov_dense(r: torch.Tensor, l0: torch.Tensor, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
     """cov[b] = (R~_b^T L0 R~_b)[idx, idx]; L0 is (D,D) or (B,D,D) with D = d or d+1 (extended covariance)."""
-    if _ag.needs_grad(r, l0):
-        raise NotImplementedError("cov_dense has no adjoint kernel yet: gradients are available for basis-state inputs "
-                                  "(cov_basis) only")
+    if _ag.needs_grad(l0):
+        raise NotImplementedError("cov_dense is differentiable w.r.t. the SPTM only: the initial-state covariance is a constant")
+    if _ag.needs_grad(r):
+        return _ag.CovDense.apply(r, l0, idx)
     r, l0 = _f64(r, "r"), _f64(l0, "l0")
     if r.ndim == 2:
         r = r[None]

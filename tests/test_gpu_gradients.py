@@ -252,6 +252,43 @@ def test_two_wire_sptm_block_gradients():
     np.testing.assert_allclose(m.grad.cpu().numpy(), fd, rtol=2e-6, atol=2e-8)
 
 
+def test_product_state_input_gradients():
+    """Non-basis product-state inputs go through the dense conjugation (cov_dense) and its adjoint kernel."""
+    n, B = 4, 3
+    rng = np.random.default_rng(13)
+    layout, params = _random_stream(n, B, rng)
+    amp = rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))
+    amp /= np.linalg.norm(amp, axis=1, keepdims=True)
+    wires = [2, 0]
+    wq = rng.standard_normal((B, 4))
+    words, coeffs = ["ZIII", "IXXI", "IIYZ", "XYZX", "IIIX"], rng.standard_normal(5)
+    wh = rng.standard_normal(B)
+
+    def f_probs(pp):
+        r = gates.chain(_oracle_ops(layout, pp), n)
+        return float((readout.analytic_probability(r, amp, wires) * wq).sum())
+
+    def f_expval(pp):
+        r = gates.chain(_oracle_ops(layout, pp), n)
+        return float((readout.expval_pauli_sum(cv.evolved_extended_covariance(amp, r), words, coeffs) * wh).sum())
+
+    for f, kind in ((f_probs, "probs"), (f_expval, "expval")):
+        fd = finite_difference(f, params)
+        ptens = [dev(params[j], grad=True) for j in range(len(params))]
+        d = mc.NIFDevice(n)
+        from matchcake_b200.operations import ProductState
+        d.execute_generator([ProductState(amp, wires=range(n))] + _device_ops(layout, ptens), reset=True)
+        if kind == "probs":
+            out = d.analytic_probability(wires)
+            (out * dev(wq).to(out.device)).sum().backward()
+        else:
+            h = obs.Hamiltonian(list(coeffs), [obs.PauliWord({i: c for i, c in enumerate(w)}) for w in words])
+            out = d.expval(h)
+            (out * dev(wh).to(out.device)).sum().backward()
+        got = np.stack([t.grad.cpu().numpy() for t in ptens])
+        np.testing.assert_allclose(got, fd, rtol=2e-6, atol=2e-8)
+
+
 def test_dense_sptm_circuit_gradients_through_device():
     """The reference's SPTM-circuit gradchecks (tests/test_devices/test_nif_device/test_gradients/
     test_apply_mths_gradients.py:156-260): a dense SPTM with requires_grad behind a rotation gate, probabilities and a
