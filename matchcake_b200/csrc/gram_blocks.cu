@@ -7,7 +7,7 @@
 // This is exactly what FermionicPQCKernel builds when n_features <= n_qubits (depth_ = 1: rotations and fSWAPs act
 // on the same pairs, fermionic_pqc_kernel.py:183-192 -- config C5, 128 qubits = 64 blocks).  The algorithmic work
 // per Gram entry drops from d^3/3 = 5.6e6 flop to 64 x ~16 flop, and the per-sample state from 512 KB to 3 KB.
-// One thread computes 4 x 4 cells (rows ty + 16a, columns tx + 16b); a block stages 64 + 64 samples x 8 blocks through shared memory.
+// A block computes 64 x 64 cells, 8 components per shared-memory stage, on the FP64 tensor pipe (see the kernel).
 #include "common.cuh"
 
 namespace mcb200 {
@@ -24,86 +24,132 @@ struct GramBlocksArgs {
   long long ldk;
 };
 
-constexpr int GB_T = 64;   // cells per tile side
-constexpr int GB_CC = 8;   // blocks (components) per shared-memory stage
-constexpr int GB_LD = GB_CC * 6 + 2;  // sample stride 400 B = 16 mod 128: the 8 lanes of a 128-bit phase hit 8 different 16-byte slots
+constexpr int GB_TM = 128;          // row samples per block tile
+constexpr int GB_TN = 64;           // column samples per block tile
+constexpr int GB_CC = 8;            // blocks (components) per shared-memory stage
+constexpr int GB_LD = GB_CC * 8 + 4;  // doubles per staged sample: 8 per component, +4 so that the 8-byte fragment reads
+                                      // of a half warp (4 rows x 4 consecutive doubles) fall on 16 distinct bank pairs
 
-__global__ void __launch_bounds__(256) gram_blocks4_kernel(GramBlocksArgs g) {
+__device__ __forceinline__ void gb_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// Pf_4(r + q) is bilinear in the two blocks up to their own Pfaffians:
+//   Pf_4(r + q) = Pf_4(r) + Pf_4(q) + r01 q23 + r23 q01 - r02 q13 - r13 q02 + r03 q12 + r12 q03
+//               = < (r01, r02, r03, r12, r13, r23, Pf_4(r), 1), (q23, -q13, q12, q03, -q02, q01, 1, Pf_4(q)) >,
+// an inner product of length 8.  For one component the 64 x 64 cells of a tile are therefore a (64 x 8)(8 x 64) matrix
+// product: two K = 4 DMMAs per 8 x 8 cells instead of ten FP64 instructions per cell, and the operands are read as MMA
+// fragments (16 eight-byte loads per warp, component and 1024 cells instead of 48 sixteen-byte ones).  The running
+// product over the components is kept in the accumulator layout.  Block tile 128 x 64 cells, 8 warps as 4 (rows) x 2
+// (columns), 32 x 32 cells each.
+__global__ void __launch_bounds__(256, 2) gram_blocks4_kernel(GramBlocksArgs g) {
   extern __shared__ __align__(16) double gb_smem[];
-  double* sr = gb_smem;
-  double* sc = gb_smem + GB_T * GB_LD;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double* As = gb_smem;                   // GB_TM row samples    x GB_LD
+  double* Bs = gb_smem + GB_TM * GB_LD;   // GB_TN column samples x GB_LD
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2, gr = lane >> 2, tg = lane & 3;
   const long long rows = g.row_end - g.row_begin;
-  const long long rt = (rows + GB_T - 1) / GB_T, ct = (g.n1 + GB_T - 1) / GB_T;
+  const long long rt = (rows + GB_TM - 1) / GB_TM, ct = (g.n1 + GB_TN - 1) / GB_TN;
   const bool upper = g.n0 < g.n1;
   for (long long t = blockIdx.x; t < rt * ct; t += gridDim.x) {
     const long long tr = t / ct, tc = t - tr * ct;
-    const long long i0 = g.row_begin + tr * GB_T, j0 = tc * GB_T;
+    const long long i0 = g.row_begin + tr * GB_TM, j0 = tc * GB_TN;
     if (g.mode != MCB200_GRAM_FULL) {  // tile without any evaluated cell (gram_matrix.py:191-195)
-      if (!upper && j0 >= i0 + GB_T) continue;
-      if (upper && j0 + GB_T - 1 <= i0) continue;
+      if (!upper && j0 >= i0 + GB_TM) continue;
+      if (upper && j0 + GB_TN - 1 <= i0) continue;
     }
-    double acc[4][4];
+    double acc[4][4][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 1.0;
+      for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 1.0;
     for (int c0 = 0; c0 < g.C; c0 += GB_CC) {
       const int cc = min(GB_CC, g.C - c0);
       __syncthreads();
-      {  // 64 samples x (cc * 6) doubles per operand: 4 threads per sample, 2 * cc... contiguous doubles each
-        const int s = tid >> 2, seg = tid & 3;
-        const int per = (cc * 6 + 3) >> 2;  // doubles per thread (12 for a full stage)
-        const int w0 = seg * per, w1 = min(w0 + per, cc * 6);
-        const long long i = i0 + s, j = j0 + s;
-        const double* pr = g.b0 + (i * g.C + c0) * 6;
-        const double* pc = g.b1 + (j * g.C + c0) * 6;
-        for (int w = w0; w < w1; ++w) {
-          sr[s * GB_LD + w] = (i < g.row_end) ? __ldg(pr + w) : 0.0;
-          sc[s * GB_LD + w] = (j < g.n1) ? __ldg(pc + w) : 0.0;
+      // stage: 192 samples x cc components, 6 (sample, component) items per thread; the 6 block entries
+      // (x01, x02 | x03, x12 | x13, x23) become the 8-vector of the row side or of the column side.  (A register
+      // prefetch of the next stage was measured: it costs the third resident block and is slower, 55 vs 52 ms on C5.)
+      for (int it = tid; it < (GB_TM + GB_TN) * GB_CC; it += 256) {
+        const int smp = it / GB_CC, c = it - smp * GB_CC;
+        const bool is_row = smp < GB_TM;
+        const long long idx = is_row ? i0 + smp : j0 + (smp - GB_TM);
+        const bool live = c < cc && (is_row ? idx < g.row_end : idx < g.n1);
+        double2 e0 = make_double2(0.0, 0.0), e1 = e0, e2 = e0;
+        if (live) {
+          const double2* src = reinterpret_cast<const double2*>((is_row ? g.b0 : g.b1) + (idx * g.C + c0 + c) * 6);
+          e0 = __ldg(src);
+          e1 = __ldg(src + 1);
+          e2 = __ldg(src + 2);
+        }
+        const double pf = fma(e1.x, e1.y, fma(-e0.y, e2.x, e0.x * e2.y));
+        double2* dst = reinterpret_cast<double2*>((is_row ? As + smp * GB_LD : Bs + (smp - GB_TM) * GB_LD) + c * 8);
+        if (is_row) {
+          dst[0] = e0;
+          dst[1] = e1;
+          dst[2] = e2;
+          dst[3] = make_double2(pf, live ? 1.0 : 0.0);
+        } else {
+          dst[0] = make_double2(e2.y, -e2.x);
+          dst[1] = make_double2(e1.y, e1.x);
+          dst[2] = make_double2(-e0.y, e0.x);
+          dst[3] = make_double2(live ? 1.0 : 0.0, pf);
         }
       }
       __syncthreads();
       for (int c = 0; c < cc; ++c) {
-        double r[4][6], q[4][6];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          // rows: one address per 16 lanes (broadcast); columns: consecutive samples (conflict free)
-          const double2* pr = reinterpret_cast<const double2*>(sr + (ty + 16 * a) * GB_LD + c * 6);
-          const double2* pq = reinterpret_cast<const double2*>(sc + (tx + 16 * a) * GB_LD + c * 6);
-#pragma unroll
-          for (int w = 0; w < 3; ++w) {
-            const double2 u = pr[w], v = pq[w];
-            r[a][2 * w] = u.x;
-            r[a][2 * w + 1] = u.y;
-            q[a][2 * w] = v.x;
-            q[a][2 * w + 1] = v.y;
-          }
-        }
+        double af[4][2], bf[4][2];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const double s01 = r[a][0] + q[b][0], s02 = r[a][1] + q[b][1], s03 = r[a][2] + q[b][2];
-            const double s12 = r[a][3] + q[b][3], s13 = r[a][4] + q[b][4], s23 = r[a][5] + q[b][5];
-            const double pf = fma(s03, s12, fma(-s02, s13, s01 * s23));
-            acc[a][b] *= fabs(pf);
-          }
+          for (int ks = 0; ks < 2; ++ks) af[a][ks] = As[(wm * 32 + a * 8 + gr) * GB_LD + c * 8 + ks * 4 + tg];
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) bf[b][ks] = Bs[(wn * 32 + b * 8 + gr) * GB_LD + c * 8 + ks * 4 + tg];
+        // 8 tiles at a time, all first K halves before the second ones: the two DMMAs of a tile are dependent, the
+        // tiles are not
+#pragma unroll
+        for (int a0 = 0; a0 < 4; a0 += 2) {
+          double p[2][4][2];
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              p[a][b][0] = p[a][b][1] = 0.0;
+              gb_dmma(p[a][b][0], p[a][b][1], af[a0 + a][0], bf[b][0]);
+            }
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) gb_dmma(p[a][b][0], p[a][b][1], af[a0 + a][1], bf[b][1]);
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              acc[a0 + a][b][0] *= fabs(p[a][b][0]);
+              acc[a0 + a][b][1] *= fabs(p[a][b][1]);
+            }
+        }
       }
     }
+    // accumulator layout: lane (gr, tg) holds cells (row gr, columns 2 tg, 2 tg + 1) of every 8 x 8 tile
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      const long long i = i0 + ty + 16 * a;
+      const long long i = i0 + wm * 32 + a * 8 + gr;
       if (i >= g.row_end) continue;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const long long j = j0 + tx + 16 * b;
-        if (j >= g.n1) continue;
-        if (g.mode != MCB200_GRAM_FULL && !(upper ? (j > i) : (i > j))) continue;
-        const double v = g.scale * acc[a][b];
-        g.K[i * g.ldk + j] = v;
-        if (g.mode == MCB200_GRAM_REFERENCE && j < g.n0 && i < g.n1) g.K[j * g.ldk + i] = v;  // gram_matrix.py:139-143
-      }
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const long long j = j0 + wn * 32 + b * 8 + 2 * tg + e;
+          if (j >= g.n1) continue;
+          if (g.mode != MCB200_GRAM_FULL && !(upper ? (j > i) : (i > j))) continue;
+          const double v = g.scale * acc[a][b][e];
+          g.K[i * g.ldk + j] = v;
+          if (g.mode == MCB200_GRAM_REFERENCE && j < g.n0 && i < g.n1) g.K[j * g.ldk + i] = v;  // gram_matrix.py:139-143
+        }
     }
   }
 }
@@ -130,9 +176,9 @@ extern "C" int mcb200_gram_blocks4(const double* blocks0, const double* blocks1,
   if (blocks0 == nullptr || blocks1 == nullptr || K == nullptr) return set_error("gram_blocks4: NULL pointer");
   cudaStream_t st = as_stream(stream);
   GramBlocksArgs g{blocks0, blocks1, n0, n1, C, row_begin, row_end, mode, scale, K, ldk};
-  const long long tiles = ((rows + GB_T - 1) / GB_T) * ((n1 + GB_T - 1) / GB_T);
+  const long long tiles = ((rows + GB_TM - 1) / GB_TM) * ((n1 + GB_TN - 1) / GB_TN);
   long long blocks = tiles < 8LL * kNumSMs ? tiles : 8LL * kNumSMs;
-  const size_t smem = 2 * (size_t)GB_T * GB_LD * sizeof(double);
+  const size_t smem = (size_t)(GB_TM + GB_TN) * GB_LD * sizeof(double);
   if (int rc = check_cuda(cudaFuncSetAttribute(gram_blocks4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                           "cudaFuncSetAttribute(gram_blocks4)"))
     return rc;
