@@ -2,7 +2,9 @@
 // small kernels around them.  Dispatch by matrix size:
 //   m <= 64          register-tile kernels, one warp per matrix          (pfaffian_tiles.cu / .cuh)
 //   64 < m <= 128    shared-memory-tile kernels, one block per matrix    (pfaffian_block_tiles.cu)
-//   m > 128          scalar Parlett-Reid, one block per matrix, working copy in a caller-provided global workspace
+//   128 < m <= 256   the same kernels with the tiles in an L2-resident slab of the caller's workspace
+//                    (plain matrices and Gram cells only)
+//   m > 256          scalar Parlett-Reid, one block per matrix, working copy in the caller's workspace
 //                    (plain matrices and Gram cells only; pfaffian_dev.cuh)
 // Matrices are formed on the fly from their sources so that sums / gathers never round-trip through HBM:
 //   Plain   A[i]                              utils/_pfaffian.py:78-119
@@ -164,7 +166,7 @@ static int launch_pfaffian(const Loader& loader, long long n_items, int m, doubl
 }
 
 static long long pfaffian_ws_bytes(long long n_items, int m) {
-  if (m <= kWarpKernelMaxM) return 0;
+  if (m <= kBlockTilesGlobalMaxM) return block_tiles_workspace_bytes(n_items, m);
   long long blocks = n_items < kBlockGlobalCtas ? n_items : kBlockGlobalCtas;
   return blocks * (long long)m * (m + 1) * (long long)sizeof(double);
 }
@@ -251,7 +253,7 @@ extern "C" int mcb200_pfaffian(const double* A, int64_t n, int32_t m, int32_t mo
   }
   if (A == nullptr) return set_error("pfaffian: A is NULL");
   if (m <= kTilesMaxM) return tiles_pfaffian_plain(A, n, m, mode, scale, out, st);
-  if (m <= kBlockTilesMaxM) return block_tiles_pfaffian_plain(A, n, m, mode, scale, out, st);
+  if (m <= kBlockTilesGlobalMaxM) return block_tiles_pfaffian_plain(A, n, m, mode, scale, out, workspace, st);
   PlainLoader ld{A, out, scale, mode};
   return launch_pfaffian(ld, n, m, (double*)workspace, st, "pfaffian_kernel");
 }
@@ -323,7 +325,7 @@ extern "C" int mcb200_pauli_sum_small(const double* cov, int64_t B, int32_t D, c
 
 extern "C" int64_t mcb200_gram_workspace_bytes(int64_t n0, int64_t n1, int32_t d) {
   if (d <= kTilesMaxM) return tiles_gram_workspace_bytes(n0, n1, d);
-  if (d <= kWarpKernelMaxM) return 0;
+  if (d <= kBlockTilesGlobalMaxM) return block_tiles_workspace_bytes(n0 * n1, d);
   return (int64_t)kBlockGlobalCtas * d * (d + 1) * (int64_t)sizeof(double);
 }
 
@@ -343,8 +345,9 @@ extern "C" int mcb200_gram(const double* cov0, const double* cov1, int64_t n0, i
   GramArgs g{cov0, cov1, n0, n1, d, row_begin, mode, scale, K, ldk};
   if (d <= kTilesMaxM) {
     if (int rc = tiles_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st)) return rc;
-  } else if (d <= kBlockTilesMaxM) {
-    if (int rc = block_tiles_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, st)) return rc;
+  } else if (d <= kBlockTilesGlobalMaxM) {
+    if (int rc = block_tiles_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st))
+      return rc;
   } else {
     if (workspace == nullptr) return set_error("gram: d=%d needs a workspace (mcb200_gram_workspace_bytes)", d);
     long long blocks = rows * n1 < kBlockGlobalCtas ? rows * n1 : kBlockGlobalCtas;

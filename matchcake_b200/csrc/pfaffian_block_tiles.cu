@@ -1,6 +1,7 @@
-// K3 for 64 < m <= 128: one 4-warp block per matrix, the upper 8x8 tiles held in SHARED memory in DMMA fragment layout
-// (tile t, lane l -> double2 at tiles[t * 32 + l], i.e. conflict-free 16-byte accesses), so every index is a run-time
-// value: the same code serves any m and both elimination orders.
+// K3 for 64 < m <= 256: one block per matrix, the upper 8x8 tiles held in DMMA fragment layout (tile t, lane l ->
+// double2 at tiles[t * 32 + l], i.e. conflict-free / fully coalesced 16-byte accesses) in SHARED memory for m <= 128
+// (4 warps) and in an L2-resident slab of the caller's workspace for 128 < m <= 256 (8 warps, no shared-memory limit
+// on the number of resident blocks).  Every index is a run-time value: the same code serves any m and both orders.
 //
 //  * static order (fast path): double step D eliminates the pairs (4D, 4D+1), (4D+2, 4D+3) with their natural pivots
 //    and applies both rank-2 updates as ONE K = 4 DMMA per live tile (see pfaffian_tiles.cuh for the algebra and
@@ -18,9 +19,8 @@
 
 namespace mcb200 {
 
-constexpr int kBtThreads = 128;
-constexpr int kBtMaxM = 128;
-constexpr int kBtVS = kBtMaxM + 4;  // vector stride (4 mod 16 doubles, see pfaffian_tiles.cuh)
+// MAXM (template parameter below) = 128 or 256 = number of threads of the block = capacity of the shared vectors;
+// vector stride MAXM + 4 (4 mod 16 doubles, see pfaffian_tiles.cuh)
 
 __device__ __forceinline__ int bt_idx(int MT, int ti, int tj) { return ti * MT - (ti * (ti - 1)) / 2 + (tj - ti); }
 
@@ -34,11 +34,12 @@ __device__ __forceinline__ double bt_elem(const double2* tiles, int MT, int i, i
 }
 
 // largest |vec[c]| (high words) over c in (last, m), identical in every warp; every lane of every warp takes part
+template <int MAXM>
 __device__ __forceinline__ unsigned bt_max_key(const double* vec, int last, int m) {
   const int lane = lane_id();
   unsigned key = 0u;
 #pragma unroll
-  for (int q = 0; q < kBtMaxM / 32; ++q) {
+  for (int q = 0; q < MAXM / 32; ++q) {
     const int c = lane + 32 * q;
     if (c > last && c < m) {
       const unsigned k2 = (unsigned)__double2hiint(vec[c]) & 0x7fffffffu;
@@ -54,7 +55,7 @@ __device__ __forceinline__ void bt_update(double2* tiles, int MT, int ti0, const
                                           const double* srcB, double sb, int dead) {
   const int lane = lane_id(), w = warp_id(), gr = lane >> 2;
   const int td = dead >> 3;
-  for (int ti = ti0 + w; ti < MT; ti += kBtThreads / 32) {
+  for (int ti = ti0 + w; ti < MT; ti += (int)(blockDim.x >> 5)) {
     double af = sa * srcA[8 * ti];
     if (ti == td && gr <= (dead & 7)) af = 0.0;
     double2* row = tiles + bt_idx(MT, ti, ti) * 32 + lane;
@@ -69,10 +70,12 @@ __device__ __forceinline__ void bt_update(double2* tiles, int MT, int ti0, const
   }
 }
 
-// Signed Pfaffian of matrix `item` of `src` (m <= 128), computed by the whole block; the result is valid in every thread.
-// tiles: MT(MT+1)/2 * 32 double2, vec: 4 * kBtVS doubles of shared memory.  Ends with a block barrier.
-template <class Src>
+// Signed Pfaffian of matrix `item` of `src` (m <= MAXM), computed by the whole block of MAXM threads; the result is
+// valid in every thread.  tiles: MT(MT+1)/2 * 32 double2 (shared or global), vec: 4 * (MAXM + 4) doubles of shared
+// memory.  Ends with a block barrier.
+template <int MAXM, class Src>
 __device__ double block_tiles_pfaffian(const Src& src, long long item, int m, double2* tiles, double* vec) {
+  constexpr int kBtMaxM = MAXM, kBtVS = MAXM + 4, kWords = MAXM / 32;
   const int MT = (m + 7) >> 3;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gr = lane >> 2, tg = lane & 3;
   // slots: row R+k -> slot brev2(k) (static path); the pivoted path uses the same four slots for its fragment vectors
@@ -82,7 +85,7 @@ __device__ double block_tiles_pfaffian(const Src& src, long long item, int m, do
   double* v2 = vec + 3 * kBtVS;
   {
     // ---- load: tile t, lane (gr, tg) <- (A[8ti+gr][8tj+2tg], A[8ti+gr][8tj+2tg+1]); rows/cols >= m are zero
-    for (int ti = w; ti < MT; ti += kBtThreads / 32)
+    for (int ti = w; ti < MT; ti += MAXM / 32)
       for (int tj = ti; tj < MT; ++tj)
         tiles[bt_idx(MT, ti, tj) * 32 + lane] = make_double2(src.at(item, 8 * ti + gr, 8 * tj + 2 * tg),
                                                              src.at(item, 8 * ti + gr, 8 * tj + 2 * tg + 1));
@@ -100,7 +103,7 @@ __device__ double block_tiles_pfaffian(const Src& src, long long item, int m, do
       }
       __syncthreads();
       const double piv1 = u[R + 1];
-      const unsigned k1 = bt_max_key(u, R + 1, m);
+      const unsigned k1 = bt_max_key<MAXM>(u, R + 1, m);
       if (!(fabs(piv1) >= kStaticPivotRatio * __hiloint2double((int)k1, 0)) || piv1 == 0.0) {
         done = R;
         break;
@@ -118,7 +121,7 @@ __device__ double block_tiles_pfaffian(const Src& src, long long item, int m, do
       }
       __syncthreads();
       const double piv2 = u2[R + 3];
-      const unsigned k2 = bt_max_key(u2, R + 3, m);
+      const unsigned k2 = bt_max_key<MAXM>(u2, R + 3, m);
       const bool odd = tg & 1;
       if (!(fabs(piv2) >= kStaticPivotRatio * __hiloint2double((int)k2, 0)) || piv2 == 0.0) {
         // commit the first pair alone and hand over
@@ -139,9 +142,9 @@ __device__ double block_tiles_pfaffian(const Src& src, long long item, int m, do
     // ---- pivoted continuation on the indices >= done
     if (done < m) {
       __syncthreads();
-      unsigned act[4];
+      unsigned act[kWords];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < kWords; ++q) {
         const int lo = 32 * q, hi = lo + 32;
         unsigned bits = 0u;
         if (m > lo) bits = (m >= hi) ? 0xffffffffu : ((1u << (m - lo)) - 1u);
@@ -158,7 +161,7 @@ __device__ double block_tiles_pfaffian(const Src& src, long long item, int m, do
       for (int s = 0; s < steps; ++s) {
         int r = 0;
 #pragma unroll
-        for (int q = 3; q >= 0; --q)
+        for (int q = kWords - 1; q >= 0; --q)
           if (act[q]) r = 32 * q + __ffs((int)act[q]) - 1;
         act[r >> 5] &= ~(1u << (r & 31));
         if (tid < kBtMaxM) rowbuf[tid] = (tid < m && is_act(tid)) ? bt_elem(tiles, MT, r, tid) : 0.0;
@@ -187,7 +190,7 @@ __device__ double block_tiles_pfaffian(const Src& src, long long item, int m, do
         {
           int cnt = 0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < kWords; ++q) {
             unsigned mask = act[q];
             const int lo = 32 * q;
             if (p <= lo) mask = 0u;
@@ -228,20 +231,23 @@ __device__ double block_tiles_pfaffian(const Src& src, long long item, int m, do
   }
 }
 
-template <class Src>
-__global__ void __launch_bounds__(kBtThreads) pfaffian_block_tiles_kernel(Src src, long long n_items, int m, int out_mode,
-                                                                           double scale, double* out) {
+// GLOBAL = false: tiles in dynamic shared memory (m <= 128).  GLOBAL = true: tiles in the block's slab of `slabs`
+// (gridDim.x slabs of MT(MT+1)/2 * 512 bytes, L2 resident), only the four vectors in shared memory.
+template <class Src, int MAXM, bool GLOBAL>
+__global__ void __launch_bounds__(MAXM) pfaffian_block_tiles_kernel(Src src, long long n_items, int m, int out_mode,
+                                                                     double scale, double* out, double2* slabs) {
   extern __shared__ __align__(16) unsigned char bt_smem[];
   const int MT = (m + 7) >> 3, NT = MT * (MT + 1) / 2;
-  double2* tiles = reinterpret_cast<double2*>(bt_smem);
-  double* vec = reinterpret_cast<double*>(tiles + NT * 32);  // 4 vectors of kBtVS doubles
+  double2* tiles = GLOBAL ? slabs + (size_t)blockIdx.x * NT * 32 : reinterpret_cast<double2*>(bt_smem);
+  double* vec = GLOBAL ? reinterpret_cast<double*>(bt_smem)
+                       : reinterpret_cast<double*>(reinterpret_cast<double2*>(bt_smem) + NT * 32);
   for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const double pf = block_tiles_pfaffian(src, item, m, tiles, vec);
+    const double pf = block_tiles_pfaffian<MAXM>(src, item, m, tiles, vec);
     if (threadIdx.x == 0) out[item] = scale * (out_mode == MCB200_PF_SIGNED ? pf : fabs(pf));
   }
 }
 
-// Gram cells for 64 < d <= 128: one block per evaluated cell (i, j), matrix cov0[i] + cov1[j] (gram_matrix.py rules as in
+// Gram cells for 64 < d <= 256: one block per evaluated cell (i, j), matrix cov0[i] + cov1[j] (gram_matrix.py rules as in
 // the other Gram kernels: only i > j, or j > i when n0 < n1, unless FULL; REFERENCE mirrors the value).
 struct GramPairSrc {
   const double* a;
@@ -267,17 +273,19 @@ struct GramBtArgs {
   long long ldk;
 };
 
-__global__ void __launch_bounds__(kBtThreads) gram_block_tiles_kernel(GramBtArgs g) {
+template <int MAXM, bool GLOBAL>
+__global__ void __launch_bounds__(MAXM) gram_block_tiles_kernel(GramBtArgs g, double2* slabs) {
   extern __shared__ __align__(16) unsigned char bt_smem[];
   const int m = g.d, MT = (m + 7) >> 3, NT = MT * (MT + 1) / 2;
-  double2* tiles = reinterpret_cast<double2*>(bt_smem);
-  double* vec = reinterpret_cast<double*>(tiles + NT * 32);
+  double2* tiles = GLOBAL ? slabs + (size_t)blockIdx.x * NT * 32 : reinterpret_cast<double2*>(bt_smem);
+  double* vec = GLOBAL ? reinterpret_cast<double*>(bt_smem)
+                       : reinterpret_cast<double*>(reinterpret_cast<double2*>(bt_smem) + NT * 32);
   const bool upper = g.n0 < g.n1;
   for (long long cell = blockIdx.x; cell < g.rows * g.n1; cell += gridDim.x) {
     const long long i = g.row_begin + cell / g.n1, j = cell % g.n1;
     if (g.mode != MCB200_GRAM_FULL && !(upper ? (j > i) : (i > j))) continue;
     GramPairSrc src{g.cov0 + i * (long long)m * m, g.cov1 + j * (long long)m * m, m};
-    const double pf = block_tiles_pfaffian(src, 0, m, tiles, vec);
+    const double pf = block_tiles_pfaffian<MAXM>(src, 0, m, tiles, vec);
     if (threadIdx.x == 0) {
       const double val = g.scale * fabs(pf);
       g.K[i * g.ldk + j] = val;
@@ -286,52 +294,81 @@ __global__ void __launch_bounds__(kBtThreads) gram_block_tiles_kernel(GramBtArgs
   }
 }
 
+// blocks that share the L2-resident slabs of the large variant (4 per SM = 160 MB at m = 256; the variant is bound by L2
+// bandwidth -- ~11 MB of tile traffic per 256 x 256 matrix -- so more resident blocks only add 7 %)
+constexpr long long kBtGlobalCtas = 4LL * kNumSMs;
+
+long long block_tiles_workspace_bytes(long long n_items, int m) {
+  if (m <= 128) return 0;
+  const int MT = (m + 7) / 8, NT = MT * (MT + 1) / 2;
+  const long long ctas = n_items < kBtGlobalCtas ? n_items : kBtGlobalCtas;
+  return ctas * (long long)NT * 32 * (long long)sizeof(double2);
+}
+
 template <class Src>
 static int launch_block_tiles(const Src& src, long long n_items, int m, int out_mode, double scale, double* out,
-                              cudaStream_t st, const char* what) {
+                              void* workspace, cudaStream_t st, const char* what) {
   if (n_items == 0) return 0;
   const int MT = (m + 7) / 8, NT = MT * (MT + 1) / 2;
-  const size_t smem = (size_t)NT * 32 * sizeof(double2) + 4 * (size_t)kBtVS * sizeof(double);
-  auto kernel = pfaffian_block_tiles_kernel<Src>;
-  if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                          "cudaFuncSetAttribute(pfaffian_block_tiles)"))
-    return rc;
-  const long long cap = 6LL * kNumSMs;
-  kernel<<<(unsigned)(n_items < cap ? n_items : cap), kBtThreads, smem, st>>>(src, n_items, m, out_mode, scale, out);
+  if (m <= 128) {
+    const size_t smem = (size_t)NT * 32 * sizeof(double2) + 4 * (size_t)(128 + 4) * sizeof(double);
+    auto kernel = pfaffian_block_tiles_kernel<Src, 128, false>;
+    if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(pfaffian_block_tiles)"))
+      return rc;
+    const long long cap = 6LL * kNumSMs;
+    kernel<<<(unsigned)(n_items < cap ? n_items : cap), 128, smem, st>>>(src, n_items, m, out_mode, scale, out, nullptr);
+    return check_launch(what);
+  }
+  if (workspace == nullptr) return set_error("%s: m=%d needs a workspace (see *_workspace_bytes)", what, m);
+  const size_t smem = 4 * (size_t)(256 + 4) * sizeof(double);
+  const long long ctas = n_items < kBtGlobalCtas ? n_items : kBtGlobalCtas;
+  pfaffian_block_tiles_kernel<Src, 256, true><<<(unsigned)ctas, 256, smem, st>>>(src, n_items, m, out_mode, scale, out,
+                                                                                  (double2*)workspace);
   return check_launch(what);
 }
 
 int block_tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
-                     long long row_end, int mode, double scale, double* K, long long ldk, cudaStream_t st) {
+                     long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,
+                     cudaStream_t st) {
   const long long rows = row_end - row_begin;
   if (rows <= 0 || n1 <= 0) return 0;
   const int MT = (d + 7) / 8, NT = MT * (MT + 1) / 2;
-  const size_t smem = (size_t)NT * 32 * sizeof(double2) + 4 * (size_t)kBtVS * sizeof(double);
-  if (int rc = check_cuda(cudaFuncSetAttribute(gram_block_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)smem), "cudaFuncSetAttribute(gram_block_tiles)"))
-    return rc;
   GramBtArgs g{cov0, cov1, n0, n1, d, row_begin, rows, mode, scale, K, ldk};
-  const long long cells = rows * n1, cap = 6LL * kNumSMs;
-  gram_block_tiles_kernel<<<(unsigned)(cells < cap ? cells : cap), kBtThreads, smem, st>>>(g);
+  const long long cells = rows * n1;
+  if (d <= 128) {
+    const size_t smem = (size_t)NT * 32 * sizeof(double2) + 4 * (size_t)(128 + 4) * sizeof(double);
+    auto kernel = gram_block_tiles_kernel<128, false>;
+    if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(gram_block_tiles)"))
+      return rc;
+    const long long cap = 6LL * kNumSMs;
+    kernel<<<(unsigned)(cells < cap ? cells : cap), 128, smem, st>>>(g, nullptr);
+    return check_launch("gram_block_tiles_kernel");
+  }
+  if (workspace == nullptr) return set_error("gram: d=%d needs a workspace (mcb200_gram_workspace_bytes)", d);
+  const size_t smem = 4 * (size_t)(256 + 4) * sizeof(double);
+  const long long ctas = cells < kBtGlobalCtas ? cells : kBtGlobalCtas;
+  gram_block_tiles_kernel<256, true><<<(unsigned)ctas, 256, smem, st>>>(g, (double2*)workspace);
   return check_launch("gram_block_tiles_kernel");
 }
 
-int block_tiles_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out,
+int block_tiles_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out, void* workspace,
                                cudaStream_t st) {
   PlainSrc s{A, m};
-  return launch_block_tiles(s, n, m, mode, scale, out, st, "pfaffian_block_tiles_kernel");
+  return launch_block_tiles(s, n, m, mode, scale, out, workspace, st, "pfaffian_block_tiles_kernel");
 }
 
 int block_tiles_pfaffian_probs(const double* cov, const int8_t* outcomes, long long B, int Q, int k, double* out,
                                cudaStream_t st) {
   ProbsSrc s{cov, outcomes, Q, k, 2 * k};
-  return launch_block_tiles(s, B * Q, 2 * k, MCB200_PF_ABS, ldexp(1.0, -k), out, st, "probs_block_tiles_kernel");
+  return launch_block_tiles(s, B * Q, 2 * k, MCB200_PF_ABS, ldexp(1.0, -k), out, nullptr, st, "probs_block_tiles_kernel");
 }
 
 int block_tiles_pfaffian_sector(const double* cov, long long B, int D, const int32_t* index_sets, int T, int s,
                                 double* feats, cudaStream_t st) {
   SectorSrc src{cov, index_sets, D, T, s};
-  return launch_block_tiles(src, B * T, s, MCB200_PF_SIGNED, 1.0, feats, st, "sector_block_tiles_kernel");
+  return launch_block_tiles(src, B * T, s, MCB200_PF_SIGNED, 1.0, feats, nullptr, st, "sector_block_tiles_kernel");
 }
 
 }  // namespace mcb200

@@ -12,16 +12,20 @@ int tiles_pfaffian_probs(const double* cov, const int8_t* outcomes, long long B,
                          cudaStream_t st);
 int tiles_pfaffian_sector(const double* cov, long long B, int D, const int32_t* index_sets, int T, int s,
                           double* feats, cudaStream_t st);
-// 64 < m <= 128: block-per-matrix variant with the tiles in shared memory (pfaffian_block_tiles.cu)
+// 64 < m <= 128: block-per-matrix variant with the tiles in shared memory; 128 < m <= 256: tiles in an L2-resident slab
+// of the caller's workspace, plain matrices and Gram cells only (pfaffian_block_tiles.cu)
 constexpr int kBlockTilesMaxM = 128;
-int block_tiles_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out,
+constexpr int kBlockTilesGlobalMaxM = 256;
+long long block_tiles_workspace_bytes(long long n_items, int m);
+int block_tiles_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out, void* workspace,
                                cudaStream_t st);
 int block_tiles_pfaffian_probs(const double* cov, const int8_t* outcomes, long long B, int Q, int k, double* out,
                                cudaStream_t st);
 int block_tiles_pfaffian_sector(const double* cov, long long B, int D, const int32_t* index_sets, int T, int s,
                                 double* feats, cudaStream_t st);
 int block_tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
-                     long long row_end, int mode, double scale, double* K, long long ldk, cudaStream_t st);
+                     long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,
+                     cudaStream_t st);
 long long tiles_gram_workspace_bytes(long long n0, long long n1, int d);
 int tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
                long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,

@@ -320,7 +320,7 @@ def test_sector_features_random_pauli_sums(n, terms):
     np.testing.assert_allclose(total.cpu().numpy(), ref, rtol=RTOL, atol=1e-12)
 
 
-@pytest.mark.parametrize("m", [4, 8, 12, 16, 24, 32, 40, 48, 64, 66, 80, 100, 128])
+@pytest.mark.parametrize("m", [4, 8, 12, 16, 24, 32, 40, 48, 64, 66, 80, 100, 128, 130, 192, 256])
 def test_pfaffian_static_path_hand_over(m):
     """The tile Pfaffian eliminates pairs (2s, 2s+1) in place while the natural pivot passes its guard and hands the
     remaining Schur complement to the pivoted routine otherwise: force the hand-over at every possible pair (zero and
@@ -334,8 +334,9 @@ def test_pfaffian_static_path_hand_over(m):
             a = random_skew(rng, (m, m))
             a[2 * s, 2 * s + 1], a[2 * s + 1, 2 * s] = eps, -eps
             mats.append(a)
-    # pivots that vanish only AFTER earlier eliminations (the natural pivot of the Schur complement is zero)
-    for s in range(1, m // 2):
+    # pivots that vanish only AFTER earlier eliminations (the natural pivot of the Schur complement is zero); not for the
+    # last pair: that matrix is singular and its "Pfaffian" is rounding noise in every implementation
+    for s in range(1, m // 2 - 1):
         a = random_skew(rng, (m, m))
         lead = a[:2 * s, :2 * s]
         b12 = a[:2 * s, 2 * s:2 * s + 2]
@@ -346,7 +347,8 @@ def test_pfaffian_static_path_hand_over(m):
     a_np = np.stack(mats)
     ref = pfaffian.pfaffian_signed(a_np)
     out = mops.pfaffian(dev(a_np), signed=True).cpu().numpy()
-    np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
+    # these matrices are ill conditioned on purpose; two different pivot orders agree to ~1e-9 at m = 256
+    np.testing.assert_allclose(out, ref, rtol=1e-9 if m <= 128 else 1e-8, atol=1e-12 * np.abs(ref).max())
 
 
 @pytest.mark.parametrize("n,terms,B", [(5, 40, 4), (9, 200, 3), (4, 300, 70)])
@@ -408,7 +410,7 @@ def test_sptm_matmul(n, batch, ta, tb):
 
 
 # ------------------------------------------------------------------ Gram
-@pytest.mark.parametrize("n,shape", [(4, (13, 13)), (4, (9, 14)), (4, (14, 9)), (16, (10, 10)), (32, (6, 6)), (40, (5, 6)), (64, (4, 4)), (70, (3, 4))])
+@pytest.mark.parametrize("n,shape", [(4, (13, 13)), (4, (9, 14)), (4, (14, 9)), (16, (10, 10)), (32, (6, 6)), (40, (5, 6)), (64, (4, 4)), (70, (3, 4)), (128, (3, 3))])
 def test_gram_matches_reference_formulation(n, shape):
     from matchcake_b200 import ops as mops
 
