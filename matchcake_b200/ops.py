@@ -291,6 +291,18 @@ def probs(cov: torch.Tensor, outcomes: torch.Tensor, normalize: bool = False) ->
     Q, k = outcomes.shape
     if m != 2 * k:
         raise ValueError("cov must be (B, 2k, 2k) for outcomes (Q, k)")
+    if m > 128:
+        # more than 64 measured wires: the fused gather kernels stop at 128 x 128; form cov + Lambda_y explicitly (one
+        # outcome at a time) and use the large-matrix Pfaffian kernels
+        sgn = outcomes.to(torch.float64) * 2.0 - 1.0                       # (Q, k): +1 for bit 1, -1 for bit 0
+        ev = torch.arange(0, m, 2, device=cov.device)
+        out = torch.empty((B, Q), dtype=torch.float64, device=cov.device)
+        for q in range(Q):
+            mat = cov.clone()
+            mat[:, ev, ev + 1] += sgn[q]
+            mat[:, ev + 1, ev] -= sgn[q]
+            out[:, q] = pfaffian(mat, signed=False, scale=2.0 ** -k)
+        return out / out.sum(dim=1, keepdim=True) if normalize else out
     out = torch.empty((B, Q), dtype=torch.float64, device=cov.device)
     check(_lib.load().mcb200_probs(_ptr(cov), _ptr(outcomes), B, Q, k, int(normalize), _ptr(out), _stream()))
     return out

@@ -47,7 +47,7 @@ def test_readme_circuit_joss_value():
     assert dev.apply_metadata["n_contracted_operations"] == 2  # two layers under the neighbours strategy
 
 
-@pytest.mark.parametrize("n,B", [(4, 17), (16, 128), (9, 3), (32, 5), (33, 4), (48, 3), (64, 2)])
+@pytest.mark.parametrize("n,B", [(4, 17), (16, 128), (9, 3), (32, 5), (33, 4), (48, 3), (64, 2), (80, 2), (128, 2)])
 def test_batched_projector_expval_and_sptm(n, B):
     rng = np.random.default_rng(n)
     p = rng.uniform(0, 2 * np.pi, (B, 2))
