@@ -64,13 +64,10 @@ __global__ void __launch_bounds__(256) sample_kernel(const double* __restrict__ 
       }
       const double inv = 1.0 / piv;
       // trailing block: A[r][c] += (v_r u_c - u_r v_c) / piv,  u = row r0, v = row r1  (r1 < r < c)
-      const int t = m - r1 - 1;
-      for (int e = lane; e < t * t; e += 32) {
-        const int ri = e / t, ci = e - ri * t;
-        if (ri < ci) {
-          const int r = r1 + 1 + ri, c = r1 + 1 + ci;
-          A[r * ld + c] += (A[r1 * ld + r] * A[r0 * ld + c] - A[r0 * ld + r] * A[r1 * ld + c]) * inv;
-        }
+      // (row by row, lanes over the columns to the right of the diagonal: no index arithmetic beyond an add)
+      for (int r = r1 + 1; r < m - 1; ++r) {
+        const double vr = A[r1 * ld + r] * inv, ur = A[r0 * ld + r] * inv;
+        for (int c = r + 1 + lane; c < m; c += 32) A[r * ld + c] += vr * A[r0 * ld + c] - ur * A[r1 * ld + c];
       }
       __syncwarp();
     }
