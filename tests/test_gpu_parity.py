@@ -454,9 +454,15 @@ def test_errors_are_loud():
         mops.pfaffian(torch.zeros((2, 4, 4), dtype=torch.float64))  # CPU tensor: no CPU path
     with pytest.raises(ValueError):
         mops.CompiledCircuit(3, [mops.GateSpec(mops.GATE_RXRX, 2, 3, 0)], 2)
-    with pytest.raises(Mcb200Error):
-        mops.probs(torch.zeros((1, 140, 140), dtype=torch.float64, device="cuda"),
-                   torch.zeros((1, 70), dtype=torch.int8, device="cuda"))
+    with pytest.raises(Mcb200Error):  # Pauli sectors beyond 128 Majorana operators are not supported
+        mops.sector_features(torch.zeros((1, 140, 140), dtype=torch.float64, device="cuda"),
+                             torch.arange(130, dtype=torch.int32, device="cuda")[None])
+    with pytest.raises(Mcb200Error):  # the C entry point itself stops at 64 measured wires (ops.probs composes beyond)
+        from matchcake_b200 import _lib
+        cov = torch.zeros((1, 140, 140), dtype=torch.float64, device="cuda")
+        oc = torch.zeros((1, 70), dtype=torch.int8, device="cuda")
+        out = torch.zeros((1, 1), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().mcb200_probs(cov.data_ptr(), oc.data_ptr(), 1, 1, 70, 0, out.data_ptr(), None))
 
 
 def test_matchgate_sptm_kernel():
