@@ -173,7 +173,11 @@ int mcb200_pauli_sum_small(const double* cov, int64_t B, int32_t D, const int32_
 /* ------------------------------------------------------------------ fused projector expval */
 /* out[b] = <y| rho_b |y> on ALL wires for the circuit applied to the basis state |bits>:
  * one kernel, SPTM columns + covariance + Pfaffian stay on chip (config C2 of BASELINE.json).
- * Replaces the whole QNode execution path of SURVEY.md section 3.1. */
+ * Replaces the whole QNode execution path of SURVEY.md section 3.1.
+ * Up to 32 qubits this is the warp-per-instance kernel the benchmark measures.  For 33 .. 59 qubits the entry point
+ * still works (block-per-instance kernel, scalar Pfaffian) but the three-call sequence mcb200_circuit_columns ->
+ * mcb200_cov_basis -> mcb200_probs is 1.6-2.5x faster (tile Pfaffians, DMMA conjugation) and has no size limit below
+ * 64 qubits; it needs caller-provided buffers for X and cov, which is why it is not hidden behind this signature. */
 int mcb200_circuit_expval_projector(const mcb200_circuit_t* circuit_host, const double* params,
                                     int64_t B, const int8_t* init_bits, const int8_t* target_bits,
                                     double* out, void* stream);

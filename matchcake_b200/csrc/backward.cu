@@ -22,7 +22,8 @@ namespace mcb200 {
 
 // ---------------------------------------------------------------------------------------------- K3 adjoint
 // In-place inverse of the m x m matrix A (m <= 128, leading dimension ld odd) by one warp.  False if singular.
-__device__ bool warp_inverse_inplace(double* A, int m, int ld, int* perm) {
+__device__ bool warp_inverse_inplace(double* __restrict__ A, int m, int ld, int* __restrict__ perm,
+                                     double* __restrict__ colk) {
   const int lane = lane_id();
   double pmax = 0.0, pmin = 1e300;
   for (int k = 0; k < m; ++k) {
@@ -72,10 +73,14 @@ __device__ bool warp_inverse_inplace(double* A, int m, int ld, int* perm) {
         A[k * ld + c] = rk[q];
       }
     }
+    // the multipliers (column k) go to a separate vector first, so that the row updates below carry no hazard between
+    // iterations and need no barrier: the rows are independent and the loop pipelines
+    for (int i = lane; i < m; i += 32) colk[i] = A[i * ld + k];
+    __syncwarp();
+#pragma unroll 4
     for (int i = 0; i < m; ++i) {
       if (i == k) continue;
-      const double f = A[i * ld + k];  // broadcast read; the owner of column k overwrites it below
-      __syncwarp();
+      const double f = colk[i];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int c = lane + 32 * q;
@@ -135,8 +140,9 @@ __global__ void __launch_bounds__(128) pfaffian_backward_kernel(Src src, Sink si
   extern __shared__ double smem[];
   const int ld = m | 1;
   const int warps = blockDim.x >> 5;
-  double* A = smem + (size_t)warp_id() * ((size_t)m * ld + 64);  // + 128 ints of pivot bookkeeping
+  double* A = smem + (size_t)warp_id() * ((size_t)m * ld + 64 + 128);  // + 128 ints of pivot bookkeeping + column vector
   int* perm = reinterpret_cast<int*>(A + (size_t)m * ld);
+  double* colk = A + (size_t)m * ld + 64;
   const int lane = lane_id();
   for (long long item = (long long)blockIdx.x * warps + warp_id(); item < n_items;
        item += (long long)gridDim.x * warps) {
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(128) pfaffian_backward_kernel(Src src, Sink si
       A[i * ld + j] = src.at(item, i, j);
     }
     __syncwarp();
-    const bool ok = warp_inverse_inplace(A, m, ld, perm);
+    const bool ok = warp_inverse_inplace(A, m, ld, perm, colk);
     __syncwarp();
     for (int e = lane; e < m * m; e += 32) {
       const int i = e / m, j = e - i * m;
@@ -317,7 +323,7 @@ template <class Src, class Sink>
 static int launch_pf_backward(const Src& src, const Sink& sink, long long n_items, int m, const double* out,
                               const double* gout, cudaStream_t st, const char* what) {
   if (n_items == 0) return 0;
-  const size_t per_warp = ((size_t)m * (m | 1) + 64) * sizeof(double);
+  const size_t per_warp = ((size_t)m * (m | 1) + 64 + 128) * sizeof(double);
   int warps = (int)((200 * 1024) / per_warp);
   if (warps > 4) warps = 4;
   if (warps < 1) return set_error("%s: m=%d does not fit shared memory", what, m);
