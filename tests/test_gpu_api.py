@@ -274,3 +274,16 @@ def test_block_factorised_gram_equals_dense_and_oracle(n, nf, rot, ent):
     # a depth-2 ansatz couples the pairs: no factorisation
     k2 = FermionicPQCKernel(n_qubits=4, rotations="X,Z").fit(rng.random((5, 8)))
     assert k2.depth_ == 2 and k2._block_plan() is None
+
+
+def test_plain_c_client_of_the_abi(tmp_path):
+    """tests/c/abi_client.c: a C99 program (no Python, no torch) drives the library through include/mcb200.h --
+    Pfaffian KATs, the README circuit (0.9901) fused and as the three-call sequence, error reporting."""
+    import subprocess
+
+    from tests.test_library_abi import _compile_c_client
+
+    exe = _compile_c_client(str(tmp_path / "abi_client"))
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "abi_client ok" in res.stdout

@@ -60,3 +60,35 @@ def test_no_batched_memcpy_calls_in_sources():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 for b in banned:
                     assert b not in txt, (f, b)
+
+
+def _compile_c_client(out_path):
+    """gcc (plain C99, no C++ and no Python) against include/mcb200.h, libmcb200.so and the CUDA runtime."""
+    import shutil
+    import subprocess
+
+    from matchcake_b200 import build
+
+    build.build()
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA runtime headers are not available")
+    libdir = os.path.join(ROOT, "matchcake_b200")
+    cmd = ["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_client.c"), "-o", out_path, "-L", libdir, "-lmcb200",
+           "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm", f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return out_path
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++-isms) and a C program must link against it."""
+    import subprocess
+
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "mcb200.h"\nint main(void) { return mcb200_version() < 0; }\n')
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                          "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    _compile_c_client(str(tmp_path / "abi_client"))
