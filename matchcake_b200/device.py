@@ -154,7 +154,7 @@ class NonInteractingFermionicDevice:
         self._compiled = None
         self._batched = False
         if self._wires is not None:
-            self._state_prep_op = ProductState.from_basis_state(np.zeros(self.num_wires, dtype=int), wires=self.wires)
+            self._state_prep_op = self._default_state()
 
     # ------------------------------------------------------------------ bookkeeping
     @property
@@ -191,7 +191,14 @@ class NonInteractingFermionicDevice:
         self._samples = None
         self.apply_metadata = defaultdict()
         if self._wires is not None:
-            self._state_prep_op = ProductState.from_basis_state(np.zeros(self.num_wires, dtype=int), wires=self.wires)
+            self._state_prep_op = self._default_state()
+
+    def _default_state(self) -> ProductState:
+        """|0..0> on the device wires (one immutable record per device, reused by every reset)."""
+        st = getattr(self, "_zero_state", None)
+        if st is None or len(st.wires) != self.num_wires:
+            st = self._zero_state = ProductState.from_basis_state(np.zeros(self.num_wires, dtype=int), wires=self.wires)
+        return st
 
     def _wire_index(self, w) -> int:
         try:
@@ -243,7 +250,7 @@ class NonInteractingFermionicDevice:
             all_wires = sorted(set(w for op in ops for w in _wires_tuple(getattr(op, "wires", ()))))
             assert len(all_wires) > 1, "At least two wires are required for this device."
             self._wires = tuple(all_wires)
-            self._state_prep_op = ProductState.from_basis_state(np.zeros(self.num_wires, dtype=int), wires=self.wires)
+            self._state_prep_op = self._default_state()
         n_ops = 0
         new_ops: List[Operation] = []
         for i, op in enumerate(ops):

@@ -612,15 +612,21 @@ class ProductState(Operation):
 
     @property
     def is_basis_state(self):
-        s = self.data[0]
-        r = np.all((np.abs(s[..., 0]) < self.ATOL) | (np.abs(s[..., 1]) < self.ATOL), axis=-1)
-        return bool(r) if self.batch_size is None else r
+        cached = getattr(self, "_is_basis_cache", None)  # the amplitudes of a state-prep record never change
+        if cached is None:
+            s = self.data[0]
+            r = np.all((np.abs(s[..., 0]) < self.ATOL) | (np.abs(s[..., 1]) < self.ATOL), axis=-1)
+            cached = self._is_basis_cache = bool(r) if self.batch_size is None else r
+        return cached
 
     def basis_state_bits(self) -> np.ndarray:
         if not np.all(self.is_basis_state):
             raise ValueError("ProductState is not a computational-basis state.")
-        s = self.data[0]
-        return (np.abs(s[..., 1]) > np.abs(s[..., 0])).astype(int)
+        bits = getattr(self, "_bits_cache", None)
+        if bits is None:
+            s = self.data[0]
+            bits = self._bits_cache = (np.abs(s[..., 1]) > np.abs(s[..., 0])).astype(int)
+        return bits
 
     def bloch(self):
         s = self.data[0]
