@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the matchgate-circuit contraction hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl ours|reference]
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic input:
   c2 (default)  N=16 README circuit (CompRxRx/RyRy/RzRz + fSWAP), projector expval, batch 65536 per GPU
@@ -10,6 +10,10 @@ One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one
                 one all-gather -> Gram entries / s           (configs[2], strong scaling)
   c4            N=64 depth-64 brickwork, qml.probs over 8 wires (256 outcomes), batch 16384 per GPU
                 -> marginal distributions / s                (configs[3])
+  c5            N=128 Nystroem Gram: 4096 landmarks (square) + 262144 x 4096 (transform), block-factorised
+                -> Gram entries / s                          (configs[4], strong scaling)
+`value` is timed with CUDA events on inputs resident in HBM (a rotating pool larger than L2 for c2); `e2e` goes through
+the public API (NonInteractingFermionicDevice / FermionicPQCKernel) from pinned HOST buffers with the result read back.
 `--impl reference` times the reference's CPU op sequence (oracle/ref_torch.py; the reference itself cannot be
 installed in this image) on the host cores with the same metric / unit / config keys.
 """
