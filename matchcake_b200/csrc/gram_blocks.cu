@@ -60,11 +60,13 @@ __global__ void __launch_bounds__(256, 2) gram_blocks4_kernel(GramBlocksArgs g) 
       if (!upper && j0 >= i0 + GB_TM) continue;
       if (upper && j0 + GB_TN - 1 <= i0) continue;
     }
-    double acc[4][4][2];
+    double acc[4][4][2], pend[4][2];  // running products; results of the unit whose multiply is still outstanding
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 1.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) pend[b][0] = pend[b][1] = 1.0;
     for (int c0 = 0; c0 < g.C; c0 += GB_CC) {
       const int cc = min(GB_CC, g.C - c0);
       __syncthreads();
@@ -108,31 +110,34 @@ __global__ void __launch_bounds__(256, 2) gram_blocks4_kernel(GramBlocksArgs g) 
         for (int b = 0; b < 4; ++b)
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) bf[b][ks] = Bs[(wn * 32 + b * 8 + gr) * GB_LD + c * 8 + ks * 4 + tg];
-        // 8 tiles at a time, all first K halves before the second ones: the two DMMAs of a tile are dependent, the
-        // tiles are not
+        // Software pipeline over the four 8-row units of the patch: the DMMAs of unit a are issued before the
+        // running products are multiplied by the results of unit a - 1 (unit 3 of the previous component for a = 0),
+        // so no multiply waits on a tensor instruction that has just been issued.
 #pragma unroll
-        for (int a0 = 0; a0 < 4; a0 += 2) {
-          double p[2][4][2];
+        for (int a = 0; a < 4; ++a) {
+          double p[4][2];
 #pragma unroll
-          for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 4; ++b) {
+            p[b][0] = p[b][1] = 0.0;
+            gb_dmma(p[b][0], p[b][1], af[a][0], bf[b][0]);
+          }
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              p[a][b][0] = p[a][b][1] = 0.0;
-              gb_dmma(p[a][b][0], p[a][b][1], af[a0 + a][0], bf[b][0]);
-            }
+          for (int b = 0; b < 4; ++b) gb_dmma(p[b][0], p[b][1], af[a][1], bf[b][1]);
 #pragma unroll
-          for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) gb_dmma(p[a][b][0], p[a][b][1], af[a0 + a][1], bf[b][1]);
-#pragma unroll
-          for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-              acc[a0 + a][b][0] *= fabs(p[a][b][0]);
-              acc[a0 + a][b][1] *= fabs(p[a][b][1]);
-            }
+          for (int b = 0; b < 4; ++b) {
+            acc[(a + 3) & 3][b][0] *= fabs(pend[b][0]);
+            acc[(a + 3) & 3][b][1] *= fabs(pend[b][1]);
+            pend[b][0] = p[b][0];
+            pend[b][1] = p[b][1];
+          }
         }
       }
+    }
+    // drain the pipeline: the last unit (a = 3 of the last component) is still pending
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      acc[3][b][0] *= fabs(pend[b][0]);
+      acc[3][b][1] *= fabs(pend[b][1]);
     }
     // accumulator layout: lane (gr, tg) holds cells (row gr, columns 2 tg, 2 tg + 1) of every 8 x 8 tile
 #pragma unroll
