@@ -483,14 +483,22 @@ def time_dominant_kernel(workload, env):
                                        row_range=(s, e), out=out)
     elif workload == "c3":
         kern, x_dev, ws = env["kern"], env["x_dev"], env["ws"]
-        cov = kern._x_to_cov(x_dev)
+        # NOTE: this function runs on rank 0 only -- nothing in here may be a collective (kern._x_to_cov all-gathers
+        # the per-sample covariances when several ranks are present, so the covariances are formed directly)
+        cov = mops.cov_basis(kern._x_to_sptm(x_dev), kern.n_qubits)
         from matchcake_b200 import distributed as dm
 
-        ranges = dm.balanced_row_ranges(cov.shape[0], cov.shape[0], ws)
-        s, e = ranges[0]
-        out = torch.zeros((cov.shape[0], cov.shape[0]), dtype=torch.float64, device=cov.device)
-        fn = lambda: mops.gram(cov, cov, 2.0 ** -32, mode=mops.GRAM_TRIANGLE if ws > 1 else mops.GRAM_REFERENCE,
-                               row_range=(s, e), out=out)
+        n = cov.shape[0]
+        out = torch.zeros((n, n), dtype=torch.float64, device=cov.device)
+        if ws > 1:  # rank 0's share of the triangle: its top and bottom row blocks (two launches)
+            top, bottom = dm.folded_row_blocks(n, ws)[0]
+
+            def fn():
+                for s, e in (top, bottom):
+                    if e > s:
+                        mops.gram(cov, cov, 2.0 ** -32, mode=mops.GRAM_TRIANGLE, row_range=(s, e), out=out)
+        else:
+            fn = lambda: mops.gram(cov, cov, 2.0 ** -32, mode=mops.GRAM_REFERENCE, out=out)
     else:
         circ, params, maj = env["circ"], env["params"], env["maj"]
         fn = lambda: mops.circuit_columns(circ, params, maj)

@@ -53,6 +53,52 @@ def balanced_row_ranges(n0: int, n1: int, parts: int, full: bool = False) -> Lis
     return [(int(bounds[p]), int(bounds[p + 1])) for p in range(parts)]
 
 
+def folded_row_blocks(n: int, parts: int) -> List[Tuple[Tuple[int, int], Tuple[int, int]]]:
+    """Square triangular Gram: rank r gets a block of rows from the top AND the mirrored block from the bottom
+    (rows taken in the order 0, n-1, 1, n-2, ...), so that every rank holds the same number of ROWS (equal-size
+    all-gather without padding) and the same number of evaluated CELLS (row i costs i, row n-1-i costs n-1-i).
+    Returns, per rank, ((top_begin, top_end), (bottom_begin, bottom_end))."""
+    c = -(-n // parts)
+    out = []
+    for r in range(parts):
+        k0, k1 = min(r * c, n), min((r + 1) * c, n)
+        top = ((k0 + 1) // 2, (k1 + 1) // 2)
+        bottom = (n - k1 // 2, n - k0 // 2)
+        out.append((top, bottom))
+    return out
+
+
+def sharded_folded_rows(compute_rows: Callable[[int, int], torch.Tensor], n: int) -> torch.Tensor:
+    """Triangular square Gram over the ranks: each rank computes its two row blocks (``compute_rows(begin, end)`` ->
+    (end - begin, n) tensor), ONE equal-size all-gather assembles the (n, n) result."""
+    import torch.distributed as dist
+
+    rank, ws = world()
+    if ws == 1:
+        return compute_rows(0, n)
+    blocks = folded_row_blocks(n, ws)
+    c = -(-n // ws)
+    (t0, t1), (b0, b1) = blocks[rank]
+    parts = [compute_rows(t0, t1)] if t1 > t0 else []
+    if b1 > b0:
+        parts.append(compute_rows(b0, b1))
+    if not parts:  # more ranks than rows: this rank only takes part in the collective
+        parts = [compute_rows(0, 0)]
+    ref = parts[0]
+    local = torch.zeros((c,) + tuple(ref.shape[1:]), dtype=ref.dtype, device=ref.device)
+    o = 0
+    for part in parts:
+        local[o:o + part.shape[0]] = part
+        o += part.shape[0]
+    gathered = torch.empty((ws * c,) + tuple(ref.shape[1:]), dtype=ref.dtype, device=ref.device)
+    dist.all_gather_into_tensor(gathered, local)
+    out = torch.empty((n,) + tuple(ref.shape[1:]), dtype=ref.dtype, device=ref.device)
+    for r, ((s0, e0), (s1, e1)) in enumerate(blocks):
+        out[s0:e0] = gathered[r * c: r * c + (e0 - s0)]
+        out[s1:e1] = gathered[r * c + (e0 - s0): r * c + (e0 - s0) + (e1 - s1)]
+    return out
+
+
 def all_gather_rows(local: torch.Tensor, ranges: List[Tuple[int, int]], n_rows: int) -> torch.Tensor:
     """Assemble a (n_rows, ...) tensor from per-rank row blocks ``local`` = rows ranges[rank] with ONE all-gather
     (blocks are padded to the largest block so that the collective is a plain equal-size all-gather)."""

@@ -115,8 +115,17 @@ class NIFKernel(Kernel):
         return r.expand(len(x), -1, -1) if r.shape[0] == 1 else r
 
     def _x_to_cov(self, x) -> torch.Tensor:
-        """Per-sample covariance Lambda_i = R_i^T Lambda_0 R_i for the |0..0> input (n_samples, 2N, 2N)."""
-        return _ops.cov_basis(self._x_to_sptm(x), self._n_qubits)
+        """Per-sample covariance Lambda_i = R_i^T Lambda_0 R_i for the |0..0> input (n_samples, 2N, 2N).  With several
+        ranks every rank evolves its slice of the samples and one all-gather replicates the covariances (the Gram
+        cells of a rank need all of them)."""
+        rank, ws = dist_mod.world()
+        n = len(x)
+        if ws == 1 or n < 4 * ws or self._differentiating():
+            return _ops.cov_basis(self._x_to_sptm(x), self._n_qubits)
+        ranges = dist_mod.even_ranges(n, ws)
+        s, e = ranges[rank]
+        local = _ops.cov_basis(self._x_to_sptm(x[s:e]), self._n_qubits)
+        return dist_mod.all_gather_rows(local, ranges, n)
 
     @property
     def sptms_train(self) -> torch.Tensor:
@@ -183,13 +192,15 @@ class NIFKernel(Kernel):
         rank, ws = dist_mod.world()
         if ws == 1:
             return _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE)
-        ranges = dist_mod.balanced_row_ranges(n0, n1, ws, full=full)
-
         def rows(s, e):
             out = torch.zeros((n0, n1), dtype=torch.float64, device=cov0.device)
             _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_TRIANGLE, row_range=(s, e), out=out)
             return out[s:e]
 
+        if n0 == n1 and not full:
+            # square triangle: folded row blocks = equal rows AND equal cells per rank, no padding in the all-gather
+            return _ops.gram_symmetrize(dist_mod.sharded_folded_rows(rows, n0))
+        ranges = dist_mod.balanced_row_ranges(n0, n1, ws, full=full)
         k = dist_mod.sharded_rows(rows, ranges, n0)
         return k if full else _ops.gram_symmetrize(k)
 
@@ -199,13 +210,14 @@ class NIFKernel(Kernel):
         rank, ws = dist_mod.world()
         if ws == 1:
             return _ops.gram_blocks4(b0, b1, mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE)
-        ranges = dist_mod.balanced_row_ranges(n0, n1, ws, full=full)
-
         def rows(s, e):
             out = torch.zeros((n0, n1), dtype=torch.float64, device=b0.device)
             _ops.gram_blocks4(b0, b1, mode=_ops.GRAM_FULL if full else _ops.GRAM_TRIANGLE, row_range=(s, e), out=out)
             return out[s:e]
 
+        if n0 == n1 and not full:
+            return _ops.gram_symmetrize(dist_mod.sharded_folded_rows(rows, n0))
+        ranges = dist_mod.balanced_row_ranges(n0, n1, ws, full=full)
         k = dist_mod.sharded_rows(rows, ranges, n0)
         return k if full else _ops.gram_symmetrize(k)
 

@@ -176,6 +176,16 @@ def test_balanced_row_ranges_cover_and_balance():
         if n0 >= 100:
             assert max(per) <= 1.05 * sum(per) / parts + n1
     assert dist_mod.even_ranges(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    # folded blocks: a partition of the rows, equal row counts, equal cell counts
+    for n, parts in [(8192, 8), (8192, 4), (101, 3), (10, 4), (5, 8), (2, 2)]:
+        blocks = dist_mod.folded_row_blocks(n, parts)
+        rows = sorted(r for (t, b) in blocks for blk in (t, b) for r in range(*blk))
+        assert rows == list(range(n))
+        cnt = [(t[1] - t[0]) + (b[1] - b[0]) for t, b in blocks]
+        assert max(cnt) == -(-n // parts)
+        if n >= 100:
+            cost = [sum(range(*t)) + sum(range(*b)) for t, b in blocks]
+            assert max(cost) - min(c for c in cost if c) <= 2 * n
 
 
 _GLOO_WORKER = r"""
@@ -193,6 +203,10 @@ ev = dm.even_ranges(9, 2)
 vec = torch.arange(9, dtype=torch.float64) * 2
 got = dm.sharded_rows(lambda s, e: vec[s:e].clone(), ev, 9)
 assert torch.equal(got, vec)
+for n in (2, 7, 10, 33):
+    sq = torch.arange(n * n, dtype=torch.float64).reshape(n, n)
+    got = dm.sharded_folded_rows(lambda s, e: sq[s:e].clone(), n)
+    assert torch.equal(got, sq), (n, got)
 dist.barrier(); dist.destroy_process_group()
 print("ok", os.environ["RANK"])
 """
