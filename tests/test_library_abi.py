@@ -92,3 +92,10 @@ def test_header_is_plain_c_and_a_c_client_links(tmp_path):
                           "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     _compile_c_client(str(tmp_path / "abi_client"))
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md is the maintainer-facing description of the boundary: it must name every exported symbol."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared_symbols() if n not in doc and not n.endswith("_workspace_bytes")]
+    assert not missing, missing
