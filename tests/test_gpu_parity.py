@@ -124,6 +124,21 @@ def test_circuit_sptm_general_gates():
     np.testing.assert_array_equal(out, np.broadcast_to(np.eye(6), (2, 6, 6)))
 
 
+@pytest.mark.parametrize("n,m", [(20, 40), (40, 80), (64, 128), (70, 140), (6, 5)])
+def test_cov_basis_both_routes_with_excited_initial_bits(n, m):
+    """K2 for a basis state with ones in it: the shared-memory kernel (narrow panels) and the DMMA GEMM route
+    (P = E^T diag(s) O, Lambda = P - P^T; wide panels) against the oracle's R^T Lambda_0 R on a random column subset."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(n)
+    bits = rng.integers(0, 2, n)
+    r = gates.random_sptm(n, seed=n, batch_size=2)
+    cols = rng.permutation(2 * n)[:m]
+    got = mops.cov_basis(dev(r[:, :, cols]), n, torch.as_tensor(bits, dtype=torch.int8)).cpu().numpy()
+    ref = cv.evolve(cv.covariance_matrix(cv.amplitudes_from_basis_state(bits)), r)[:, cols][:, :, cols]
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-12)
+
+
 @pytest.mark.parametrize("n", [2, 5, 16, 33, 64])
 @pytest.mark.parametrize("m", [1, 3, 8])
 def test_register_resident_chain_matches_general_kernel(n, m):
