@@ -287,3 +287,34 @@ def test_plain_c_client_of_the_abi(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "abi_client ok" in res.stdout
+
+
+def test_strategy_objects_drive_the_gpu_path():
+    """matchcake_b200.strategies: the reference's plug-in signatures (probability / expval / contraction strategy)
+    called the way its device calls them, against the oracle."""
+    from matchcake_b200 import strategies as st
+    from matchcake_b200.operations import BasisState, ProductState
+
+    n, B = 4, 3
+    rng = np.random.default_rng(21)
+    r = gates.random_sptm(n, seed=2, batch_size=B)
+    bits = np.array([1, 0, 0, 1])
+    targets = np.array([[0, 1], [1, 1], [0, 0]])
+    wires = [2, 0]
+    p = st.B200ProbabilityStrategy()(state_prep_op=BasisState(bits, wires=range(n)), target_binary_states=targets,
+                                     wires=wires, global_sptm=r, all_wires=list(range(n)))
+    ref = readout.states_probability(r, cv.amplitudes_from_basis_state(bits), targets, np.array(wires))
+    np.testing.assert_allclose(p.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    amp = rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))
+    amp /= np.linalg.norm(amp, axis=1, keepdims=True)
+    words, coeffs = ["ZIII", "IXXI", "YZZX"], rng.standard_normal(3)
+    h = obs.Hamiltonian(list(coeffs), [obs.PauliWord({i: c for i, c in enumerate(w)}) for w in words])
+    e = st.B200PfaffianExpvalStrategy()(ProductState(amp, wires=range(n)), h, global_sptm=r, all_wires=list(range(n)))
+    np.testing.assert_allclose(e.cpu().numpy(), readout.expval_pauli_sum(cv.evolved_extended_covariance(amp, r), words, coeffs),
+                               rtol=RTOL, atol=1e-12)
+    pr = rng.uniform(0, 6, (B, 2))
+    stream = [SptmCompRyRy(pr, wires=[0, 1]), SptmFSwap(wires=[1, 3]), SptmCompRxRx(pr, wires=[2, 3])]
+    out = st.B200ContractionStrategy(wires=range(n))(stream)
+    assert len(out) == 1
+    ref_r = gates.chain([Op("SptmCompRyRy", (0, 1), params=pr), Op("SptmFSwap", (1, 3)), Op("SptmCompRxRx", (2, 3), params=pr)], n)
+    np.testing.assert_allclose(out[0].matrix().cpu().numpy(), ref_r, rtol=RTOL, atol=ATOL)

@@ -223,3 +223,31 @@ def test_all_gather_rows_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_strategy_plugin_surface_contract():
+    """The reference's strategy ABCs (SURVEY 8b iii): names, required kwargs and error behaviour, no GPU needed."""
+    from matchcake_b200 import strategies as st
+    from matchcake_b200.operations import BasisState, ProductState
+
+    p = st.B200ProbabilityStrategy()
+    assert p.NAME == "B200" and p.REQUIRES_KWARGS == ["global_sptm", "all_wires"]
+    assert p.can_execute(BasisState(np.zeros(3, dtype=int), wires=range(3)))
+    assert p.can_execute(ProductState(np.tile(np.array([1.0, 0.0], dtype=complex), (3, 1)), wires=range(3)))
+    assert not p.can_execute(object())
+    with pytest.raises(ValueError, match="Missing required keyword argument: global_sptm"):
+        p(state_prep_op=None, target_binary_states=[0, 0, 0], wires=[0, 1, 2], all_wires=[0, 1, 2])
+    with pytest.raises(ValueError, match="Missing required keyword argument"):
+        st.B200PfaffianExpvalStrategy()(None, None, global_sptm=np.eye(4))
+    assert isinstance(st.get_probability_strategy("LookupTable"), st.B200ProbabilityStrategy)
+    assert isinstance(st.get_probability_strategy(p), st.B200ProbabilityStrategy)
+    with pytest.raises(ValueError):
+        st.get_probability_strategy("ExplicitSum")
+    c = st.B200ContractionStrategy()
+    assert c.get_next_operations("op-a") == [] and c.get_next_operations("op-b") == []
+    assert c._ops == ["op-a", "op-b"]
+    c.reset()
+    assert c._ops == [] and c.get_reminding() is None
+    for base in (st.ProbabilityStrategy, st.ExpvalStrategy):
+        with pytest.raises(NotImplementedError):
+            base()(state_prep_op=None, target_binary_states=None, wires=None) if base is st.ProbabilityStrategy else base()(None, None)
