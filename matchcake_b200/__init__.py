@@ -6,6 +6,6 @@ Pfaffians, and the kernel Gram-matrix builder, as hand-written sm_100a CUDA behi
 """
 from . import _lib, observables, operations, ops, utils  # noqa: F401
 from .device import DeviceError, NIFDevice, NonInteractingFermionicDevice  # noqa: F401
-from . import ml  # noqa: F401
+from . import ml, strategies  # noqa: F401
 
 __version__ = "0.1.0"
