@@ -76,6 +76,18 @@ int mcb200_version(void);
 const char* mcb200_last_error(void);
 int mcb200_device_count(void);
 
+/* Magnitude floor, sticky per calling thread.  The reference's probability read-outs are
+ * utils.pfaffian(sign=False) = torch_pfaffian.PfaffianDet = sqrt(|det A| + EPSILON), EPSILON = 1e-32
+ * (utils/_pfaffian.py:81,110-118; a process-wide global the reference mutates under a lock before every call).
+ * With floor2 > 0 every magnitude-type output v of this library -- mcb200_pfaffian (mode ABS, scale included),
+ * mcb200_probs / mcb200_probs_all (before the optional normalisation), mcb200_circuit_expval_projector,
+ * mcb200_gram / mcb200_gram_blocks4 entries -- is returned as sqrt(v^2 + floor2).  The caller converts the reference's
+ * EPSILON to output units: LookupTableStrategy (lookup_table_strategy.py:70-71, basis-state inputs, Gram) floors the
+ * probability itself (floor2 = EPSILON); ProductStateProbabilityStrategy (product_state_strategy.py:211-212) floors
+ * Pf before the 2^-k factor (floor2 = 4^-k EPSILON).  0 (the initial value) switches the floor off. */
+int mcb200_set_abs_floor(double floor2);
+double mcb200_get_abs_floor(void);
+
 /* ------------------------------------------------------------------ K1: SPTM chain */
 /* Columns of the global SPTM of a gate-list circuit: X[b] = R_b[:, cols] (d x m), one instance per
  * batch row of params (B, P).  cols = NULL -> all d columns (X = R).  Replaces the per-gate Python

@@ -7,6 +7,7 @@ namespace mcb200 {
 
 thread_local std::string g_last_error;
 std::atomic<long long> g_launch_count{0};
+thread_local double g_abs_floor2 = 0.0;
 
 int set_error(const char* fmt, ...) {
   char buf[1024];
@@ -75,6 +76,12 @@ extern "C" int mcb200_device_count(void) {
   }
   return n;
 }
+extern "C" int mcb200_set_abs_floor(double floor2) {
+  if (!(floor2 >= 0.0)) return set_error("set_abs_floor: floor2 must be >= 0");
+  g_abs_floor2 = floor2;
+  return 0;
+}
+extern "C" double mcb200_get_abs_floor(void) { return g_abs_floor2; }
 extern "C" int64_t mcb200_launch_count(void) { return g_launch_count.load(); }
 extern "C" void mcb200_reset_launch_count(void) { g_launch_count.store(0); }
 

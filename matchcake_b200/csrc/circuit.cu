@@ -191,7 +191,7 @@ __global__ void cov_basis_kernel(const double* __restrict__ X, const int8_t* bit
 // Fused: circuit -> X (d x d) -> Lambda = X^T Lambda_0 X -> + Lambda_y -> 2^-N |Pf|.   One block per instance.
 __global__ void circuit_expval_projector_kernel(CircuitDev c, const double* __restrict__ params,
                                                 const int8_t* init_bits, const int8_t* target_bits,
-                                                double* __restrict__ out) {
+                                                double floor2, double* __restrict__ out) {
   extern __shared__ double smem[];
   const int n = c.n_qubits, d = 2 * n;
   const long long b = blockIdx.x;
@@ -208,7 +208,7 @@ __global__ void circuit_expval_projector_kernel(CircuitDev c, const double* __re
     A[(2 * j) * lda + 2 * j + 1] += (target_bits != nullptr && target_bits[j]) ? 1.0 : -1.0;
   __syncthreads();
   double pf = block_pfaffian_upper(A, d, lda, red);
-  if (threadIdx.x == 0) out[b] = ldexp(fabs(pf), -n);
+  if (threadIdx.x == 0) out[b] = abs_floor(ldexp(pf, -n), floor2);
 }
 
 // Block-diagonal circuits: one THREAD per (instance, wire pair).  The pair's 4x4 SPTM block is built in registers
@@ -369,7 +369,7 @@ extern "C" int mcb200_circuit_expval_projector(const mcb200_circuit_t* circuit_h
     return rc;
   const int threads = d >= 64 ? 256 : 128;
   circuit_expval_projector_kernel<<<(unsigned)B, threads, smem, as_stream(stream)>>>(c, params, init_bits,
-                                                                                   target_bits, out);
+                                                                                   target_bits, g_abs_floor2, out);
   return check_launch("circuit_expval_projector_kernel");
 }
 

@@ -13,6 +13,9 @@ namespace mcb200 {
 
 extern thread_local std::string g_last_error;
 extern std::atomic<long long> g_launch_count;
+// Sticky per-thread option (mcb200_set_abs_floor): every magnitude-type output v (|Pf| x scale, probabilities,
+// projector expectation values, Gram entries) is returned as sqrt(v^2 + floor2).  0 = off.
+extern thread_local double g_abs_floor2;
 
 int set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
@@ -23,6 +26,11 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 constexpr int kWarp = 32;
 constexpr int kNumSMs = 148;  // B200
 constexpr int kMaxDynSmem = 227 * 1024;
+
+// torch_pfaffian.PfaffianDet returns sqrt(|det A| + EPSILON) = sqrt(Pf^2 + EPSILON) (utils/_pfaffian.py:110-118)
+__device__ __forceinline__ double abs_floor(double v, double floor2) {
+  return floor2 > 0.0 ? sqrt(fma(v, v, floor2)) : fabs(v);
+}
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }

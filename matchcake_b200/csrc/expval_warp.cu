@@ -61,7 +61,7 @@ __device__ __forceinline__ int wc_run(int code) { return (code >> 20) & 0xfff; }
 template <int MT>
 __global__ void __launch_bounds__(192, (MT <= 4 ? 3 : 1)) expval_warp_kernel(WarpCircuit wc, const double* __restrict__ params,
                                                           long long B, const int8_t* init_bits,
-                                                          const int8_t* target_bits, int gates_in_smem,
+                                                          const int8_t* target_bits, double floor2,
                                                           double* __restrict__ out) {
   using T = Tiles<MT>;
   constexpr int M = T::M;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(192, (MT <= 4 ? 3 : 1)) expval_warp_kernel(War
       }
     }
     const double pf = warp_pfaffian_tiles<MT, 0, true>(c, d, scratch);  // Lambda|_W + Lambda_y of a physical state: bounded
-    if (lane == 0) out[b] = ldexp(fabs(pf), -n);
+    if (lane == 0) out[b] = abs_floor(ldexp(pf, -n), floor2);
     __syncwarp();
   }
 }
@@ -259,7 +259,6 @@ int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long lon
   const int mt = d <= 8 ? 1 : d <= 16 ? 2 : d <= 24 ? 3 : d <= 32 ? 4 : d <= 48 ? 6 : 8;
   const int M = 8 * mt, LDX = M + 4;
   const int warps = 6;
-  const int gates_in_smem = 1;
   const size_t gate_bytes = (((size_t)h->n_gates * 2 * sizeof(int)) + 15) & ~(size_t)15;
   const size_t per_warp = ((((size_t)d * LDX + 128 + (2 * M + 4 * (M + 8))) * sizeof(double) + 64) + 15) & ~(size_t)15;
   const size_t smem = gate_bytes + warps * per_warp;
@@ -271,7 +270,7 @@ int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long lon
     if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(expval_warp)"))
       return rc;
-    kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(wc, params, B, init_bits, target_bits, gates_in_smem, out);
+    kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(wc, params, B, init_bits, target_bits, g_abs_floor2, out);
     return check_launch("expval_warp_kernel");
   };
   switch (mt) {

@@ -22,6 +22,7 @@ struct GramBlocksArgs {
   double scale;      // global factor, normally 2^-(2C) = 2^-N
   double* K;
   long long ldk;
+  double floor2;
 };
 
 constexpr int GB_TM = 128;          // row samples per block tile
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(256, 2) gram_blocks4_kernel(GramBlocksArgs g) 
           const long long j = j0 + wn * 32 + b * 8 + 2 * tg + e;
           if (j >= g.n1) continue;
           if (g.mode != MCB200_GRAM_FULL && !(upper ? (j > i) : (i > j))) continue;
-          const double v = g.scale * acc[a][b][e];
+          const double v = abs_floor(g.scale * acc[a][b][e], g.floor2);
           g.K[i * g.ldk + j] = v;
           if (g.mode == MCB200_GRAM_REFERENCE && j < g.n0 && i < g.n1) g.K[j * g.ldk + i] = v;  // gram_matrix.py:139-143
         }
@@ -180,7 +181,7 @@ extern "C" int mcb200_gram_blocks4(const double* blocks0, const double* blocks1,
   if (rows == 0 || n1 == 0) return 0;
   if (blocks0 == nullptr || blocks1 == nullptr || K == nullptr) return set_error("gram_blocks4: NULL pointer");
   cudaStream_t st = as_stream(stream);
-  GramBlocksArgs g{blocks0, blocks1, n0, n1, C, row_begin, row_end, mode, scale, K, ldk};
+  GramBlocksArgs g{blocks0, blocks1, n0, n1, C, row_begin, row_end, mode, scale, K, ldk, g_abs_floor2};
   const long long tiles = ((rows + GB_TM - 1) / GB_TM) * ((n1 + GB_TN - 1) / GB_TN);
   long long blocks = tiles < 8LL * kNumSMs ? tiles : 8LL * kNumSMs;
   const size_t smem = (size_t)(GB_TM + GB_TN) * GB_LD * sizeof(double);

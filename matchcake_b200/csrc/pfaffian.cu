@@ -23,6 +23,7 @@ struct PlainLoader {
   double* out;
   double scale;
   int mode;
+  double floor2;
   __device__ void load(long long item, double* S, int lds, int m, int tid, int nthr) const {
     const double* src = A + item * (long long)m * m;
     for (int idx = tid; idx < m * m; idx += nthr) {
@@ -31,7 +32,7 @@ struct PlainLoader {
     }
   }
   __device__ void store(long long item, double pf) const {
-    out[item] = scale * (mode == MCB200_PF_SIGNED ? pf : fabs(pf));
+    out[item] = mode == MCB200_PF_SIGNED ? scale * pf : abs_floor(scale * pf, floor2);
   }
 };
 
@@ -184,6 +185,7 @@ struct GramArgs {
   double scale;
   double* K;
   long long ldk;
+  double floor2;
 };
 
 __device__ __forceinline__ bool gram_cell_active(const GramArgs& g, long long i, long long j) {
@@ -213,19 +215,39 @@ __global__ void gram_block_global_kernel(GramArgs g, long long rows, double* wor
     }
     __syncthreads();
     double pf = block_pfaffian_upper(S, m, lds, red);
-    if (threadIdx.x == 0) gram_store(g, i, j, g.scale * fabs(pf));
+    if (threadIdx.x == 0) gram_store(g, i, j, abs_floor(g.scale * pf, g.floor2));
     __syncthreads();
   }
 }
 
-__global__ void gram_symmetrize_kernel(double* K, long long n0, long long n1, long long ldk) {
-  // gram_matrix.py:127-161: mirror the computed triangle inside the leading min(n0,n1)^2 block, diagonal := 1
-  const long long q = n0 < n1 ? n0 : n1;
-  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= q * q) return;
-  long long i = e / q, j = e - i * q;
-  if (i == j) K[i * ldk + i] = 1.0;
-  else if (n0 < n1 ? (i > j) : (j > i)) K[i * ldk + j] = K[j * ldk + i];
+// gram_matrix.py:127-161: mirror the computed triangle inside the leading min(n0,n1)^2 block, diagonal := 1.
+// One 32 x 32 tile pair per block: the source tile (bj, bi) is read row-wise (coalesced), transposed through shared
+// memory and written row-wise into the target tile (bi, bj); 8 warps, 4 rows each.
+__global__ void __launch_bounds__(256) gram_symmetrize_kernel(double* K, long long q, long long ldk, int fill_lower) {
+  __shared__ double tile[32][33];
+  // block index -> (a, b) with a <= b over the tiles of the q x q block
+  const long long nt = (q + 31) / 32;
+  long long t = blockIdx.x;
+  // row a of the upper-triangular tile enumeration holds nt - a tiles
+  long long a = (long long)((2.0 * nt + 1.0 - sqrt((2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t)) * 0.5);
+  while (a > 0 && a * nt - a * (a - 1) / 2 > t) --a;
+  while ((a + 1) * nt - (a + 1) * a / 2 <= t) ++a;
+  const long long b = a + (t - (a * nt - a * (a - 1) / 2));
+  // target tile = the one in the triangle that is NOT evaluated: upper (a, b) when the evaluated cells are i > j
+  // (n0 >= n1), lower (b, a) when they are j > i (n0 < n1)
+  const long long ti = fill_lower ? b : a, tj = fill_lower ? a : b;   // target tile (rows ti, cols tj)
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {   // source tile (tj, ti): rows 32 tj + r, cols 32 ti + tx
+    const long long i = 32 * tj + r, j = 32 * ti + tx;
+    tile[r][tx] = (i < q && j < q) ? K[i * ldk + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {   // target rows 32 ti + r, cols 32 tj + tx  <-  source[tx][r]
+    const long long i = 32 * ti + r, j = 32 * tj + tx;
+    if (i >= q || j >= q) continue;
+    if (i == j) K[i * ldk + j] = 1.0;
+    else if (fill_lower ? (i > j) : (j > i)) K[i * ldk + j] = tile[tx][r];
+  }
 }
 
 __global__ void gram_diag_kernel(GramArgs g, long long row_end) {
@@ -254,7 +276,7 @@ extern "C" int mcb200_pfaffian(const double* A, int64_t n, int32_t m, int32_t mo
   if (A == nullptr) return set_error("pfaffian: A is NULL");
   if (m <= kTilesMaxM) return tiles_pfaffian_plain(A, n, m, mode, scale, out, st);
   if (m <= kBlockTilesGlobalMaxM) return block_tiles_pfaffian_plain(A, n, m, mode, scale, out, workspace, st);
-  PlainLoader ld{A, out, scale, mode};
+  PlainLoader ld{A, out, scale, mode, g_abs_floor2};
   return launch_pfaffian(ld, n, m, (double*)workspace, st, "pfaffian_kernel");
 }
 
@@ -342,7 +364,7 @@ extern "C" int mcb200_gram(const double* cov0, const double* cov1, int64_t n0, i
   if (rows == 0 || n1 == 0) return 0;
   if (cov0 == nullptr || cov1 == nullptr || K == nullptr) return set_error("gram: NULL pointer");
   cudaStream_t st = as_stream(stream);
-  GramArgs g{cov0, cov1, n0, n1, d, row_begin, mode, scale, K, ldk};
+  GramArgs g{cov0, cov1, n0, n1, d, row_begin, mode, scale, K, ldk, g_abs_floor2};
   if (d <= kTilesMaxM) {
     if (int rc = tiles_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st)) return rc;
   } else if (d <= kBlockTilesGlobalMaxM) {
@@ -366,7 +388,8 @@ extern "C" int mcb200_gram_symmetrize(double* K, int64_t n0, int64_t n1, int64_t
   const long long q = n0 < n1 ? n0 : n1;
   if (q == 0) return 0;
   if (K == nullptr) return set_error("gram_symmetrize: K is NULL");
-  gram_symmetrize_kernel<<<(unsigned)((q * q + 255) / 256), 256, 0, as_stream(stream)>>>(K, n0, n1, ldk);
+  const long long nt = (q + 31) / 32;
+  gram_symmetrize_kernel<<<(unsigned)(nt * (nt + 1) / 2), 256, 0, as_stream(stream)>>>(K, q, ldk, n0 < n1 ? 1 : 0);
   return check_launch("gram_symmetrize_kernel");
 }
 

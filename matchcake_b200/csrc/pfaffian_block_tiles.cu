@@ -235,7 +235,8 @@ __device__ double block_tiles_pfaffian(const Src& src, long long item, int m, do
 // (gridDim.x slabs of MT(MT+1)/2 * 512 bytes, L2 resident), only the four vectors in shared memory.
 template <class Src, int MAXM, bool GLOBAL>
 __global__ void __launch_bounds__(MAXM) pfaffian_block_tiles_kernel(Src src, long long n_items, int m, int out_mode,
-                                                                     double scale, double* out, double2* slabs) {
+                                                                     double scale, double floor2, double* out,
+                                                                     double2* slabs) {
   extern __shared__ __align__(16) unsigned char bt_smem[];
   const int MT = (m + 7) >> 3, NT = MT * (MT + 1) / 2;
   double2* tiles = GLOBAL ? slabs + (size_t)blockIdx.x * NT * 32 : reinterpret_cast<double2*>(bt_smem);
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(MAXM) pfaffian_block_tiles_kernel(Src src, lon
                        : reinterpret_cast<double*>(reinterpret_cast<double2*>(bt_smem) + NT * 32);
   for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
     const double pf = block_tiles_pfaffian<MAXM>(src, item, m, tiles, vec);
-    if (threadIdx.x == 0) out[item] = scale * (out_mode == MCB200_PF_SIGNED ? pf : fabs(pf));
+    if (threadIdx.x == 0) out[item] = out_mode == MCB200_PF_SIGNED ? scale * pf : abs_floor(scale * pf, floor2);
   }
 }
 
@@ -271,6 +272,7 @@ struct GramBtArgs {
   double scale;
   double* K;
   long long ldk;
+  double floor2;
 };
 
 template <int MAXM, bool GLOBAL>
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(MAXM) gram_block_tiles_kernel(GramBtArgs g, do
     GramPairSrc src{g.cov0 + i * (long long)m * m, g.cov1 + j * (long long)m * m, m};
     const double pf = block_tiles_pfaffian<MAXM>(src, 0, m, tiles, vec);
     if (threadIdx.x == 0) {
-      const double val = g.scale * fabs(pf);
+      const double val = abs_floor(g.scale * pf, g.floor2);
       g.K[i * g.ldk + j] = val;
       if (g.mode == MCB200_GRAM_REFERENCE && j < g.n0 && i < g.n1) g.K[j * g.ldk + i] = val;  // gram_matrix.py:139-143
     }
@@ -317,13 +319,13 @@ static int launch_block_tiles(const Src& src, long long n_items, int m, int out_
                             "cudaFuncSetAttribute(pfaffian_block_tiles)"))
       return rc;
     const long long cap = 6LL * kNumSMs;
-    kernel<<<(unsigned)(n_items < cap ? n_items : cap), 128, smem, st>>>(src, n_items, m, out_mode, scale, out, nullptr);
+    kernel<<<(unsigned)(n_items < cap ? n_items : cap), 128, smem, st>>>(src, n_items, m, out_mode, scale, g_abs_floor2, out, nullptr);
     return check_launch(what);
   }
   if (workspace == nullptr) return set_error("%s: m=%d needs a workspace (see *_workspace_bytes)", what, m);
   const size_t smem = 4 * (size_t)(256 + 4) * sizeof(double);
   const long long ctas = n_items < kBtGlobalCtas ? n_items : kBtGlobalCtas;
-  pfaffian_block_tiles_kernel<Src, 256, true><<<(unsigned)ctas, 256, smem, st>>>(src, n_items, m, out_mode, scale, out,
+  pfaffian_block_tiles_kernel<Src, 256, true><<<(unsigned)ctas, 256, smem, st>>>(src, n_items, m, out_mode, scale, g_abs_floor2, out,
                                                                                   (double2*)workspace);
   return check_launch(what);
 }
@@ -334,7 +336,7 @@ int block_tiles_gram(const double* cov0, const double* cov1, long long n0, long 
   const long long rows = row_end - row_begin;
   if (rows <= 0 || n1 <= 0) return 0;
   const int MT = (d + 7) / 8, NT = MT * (MT + 1) / 2;
-  GramBtArgs g{cov0, cov1, n0, n1, d, row_begin, rows, mode, scale, K, ldk};
+  GramBtArgs g{cov0, cov1, n0, n1, d, row_begin, rows, mode, scale, K, ldk, g_abs_floor2};
   const long long cells = rows * n1;
   if (d <= 128) {
     const size_t smem = (size_t)NT * 32 * sizeof(double2) + 4 * (size_t)(128 + 4) * sizeof(double);

@@ -22,7 +22,7 @@ __device__ __forceinline__ void load_fragments(const Src& src, long long item, d
 
 template <int MT, class Src>
 __global__ void __launch_bounds__(128) pfaffian_tiles_kernel(Src src, long long n_items, int m, int out_mode,
-                                                             double scale, double* out) {
+                                                             double scale, double floor2, double* out) {
   extern __shared__ double smem[];
   double* scratch = smem + (size_t)warp_id() * Tiles<MT>::kScratch;
   const int warps = blockDim.x >> 5;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) pfaffian_tiles_kernel(Src src, long long 
     double c[Tiles<MT>::NT][2];
     load_fragments<MT>(src, item, c);
     double pf = warp_pfaffian_tiles<MT>(c, m, scratch);
-    if (lane_id() == 0) out[item] = scale * (out_mode == MCB200_PF_SIGNED ? pf : fabs(pf));
+    if (lane_id() == 0) out[item] = out_mode == MCB200_PF_SIGNED ? scale * pf : abs_floor(scale * pf, floor2);
     __syncwarp();
   }
 }
@@ -46,7 +46,7 @@ static int launch_tiles(const Src& src, long long n_items, int m, int out_mode, 
   if (blocks > cap) blocks = cap;
   auto go = [&](auto kernel, int mt) -> int {
     const size_t smem = (size_t)warps * (2 * 8 * mt + 4 * (8 * mt + 8)) * sizeof(double);
-    kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(src, n_items, m, out_mode, scale, out);
+    kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(src, n_items, m, out_mode, scale, g_abs_floor2, out);
     return check_launch(what);
   };
   if (m <= 8) return go(pfaffian_tiles_kernel<1, Src>, 1);
@@ -114,6 +114,7 @@ struct GramTileArgs {
   double scale;
   double* K;
   long long ldk;
+  double floor2;
 };
 
 // One warp per (i, j) cell.  A block of TI x TJ warps walks (row-block, column-block) tiles so that the fragments
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(32 * TI * TJ, MINB) gram_tiles_kernel(GramTile
     }
     const double pf = warp_pfaffian_tiles<MT, SR>(c, g.m, scratch, sm);
     if (lane == 0) {
-      const double v = g.scale * fabs(pf);
+      const double v = abs_floor(g.scale * pf, g.floor2);
       g.K[i * g.ldk + j] = v;
       if (g.mode == MCB200_GRAM_REFERENCE && j < g.n0 && i < g.n1) g.K[j * g.ldk + i] = v;  // gram_matrix.py:139-143
     }
@@ -193,7 +194,7 @@ static int gram_tiles_launch(const double* cov0, const double* cov1, long long n
   if (int rc = pack(cov0, n0, p0)) return rc;
   if (same) p1 = p0;
   else if (int rc = pack(cov1, n1, p1)) return rc;
-  GramTileArgs g{p0, p1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk};
+  GramTileArgs g{p0, p1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, g_abs_floor2};
   const long long rows = row_end - row_begin;
   auto launch = [&](auto kernel, int ti, int tj, int per_sm, size_t per_warp_doubles) -> int {
     const size_t smem = (size_t)ti * tj * per_warp_doubles * sizeof(double);
@@ -240,7 +241,8 @@ int tiles_gram(const double* cov0, const double* cov1, long long n0, long long n
 namespace mcb200 {
 
 __global__ void __launch_bounds__(128) probs_tree_kernel(const double* __restrict__ cov, long long B, int k,
-                                                         int normalize, int buf_doubles, double* __restrict__ out) {
+                                                         int normalize, int buf_doubles, double floor2,
+                                                         double* __restrict__ out) {
   extern __shared__ double smem[];
   const int m = 2 * k, Q = 1 << k;
   const int lane = lane_id(), warps = blockDim.x >> 5;
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(128) probs_tree_kernel(const double* __restric
     // leaves: fc[q] = prod of pivots = Pf; p = 2^-k |Pf|
     double sum = 0.0;
     for (int q = lane; q < Q; q += 32) {
-      const double p = ldexp(fabs(fc[q]), -k);
+      const double p = abs_floor(ldexp(fc[q], -k), floor2);
       fc[q] = p;
       sum += p;
     }
@@ -335,7 +337,7 @@ int tiles_probs_all(const double* cov, long long B, int k, int normalize, double
     return rc;
   long long blocks = (B + warps - 1) / warps;
   if (blocks > 16LL * kNumSMs) blocks = 16LL * kNumSMs;
-  probs_tree_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(cov, B, k, normalize, (int)buf, out);
+  probs_tree_kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(cov, B, k, normalize, (int)buf, g_abs_floor2, out);
   return check_launch("probs_tree_kernel");
 }
 

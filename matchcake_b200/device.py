@@ -139,6 +139,9 @@ class NonInteractingFermionicDevice:
         if key not in CONTRACTION_STRATEGIES:
             raise ValueError(f"Unknown contraction strategy {cs!r}; available: {sorted(k for k in CONTRACTION_STRATEGIES if k)}")
         self.contraction_strategy = CONTRACTION_STRATEGIES[key]
+        #: EPSILON of the reference's magnitude Pfaffian, sqrt(|det| + EPSILON) (utils/_pfaffian.py:81,110-118);
+        #: 0 returns the exact |Pf| (parity-forbidden outcomes are then exactly 0 instead of ~1e-16)
+        self.pfaffian_epsilon = float(kwargs.get("pfaffian_epsilon", 1e-32))
         self.torch_device = torch.device(kwargs.get("device", "cuda"))
         self.output_device = kwargs.get("output_device", "cpu")
         self.show_progress = kwargs.get("show_progress", False)
@@ -338,15 +341,18 @@ class NonInteractingFermionicDevice:
         def param_offset(p, width) -> int:
             nonlocal n_cols
             key = id(p)
-            if key in col_of:
-                return col_of[key]
+            hit = col_of.get(key)
+            if hit is not None and hit[1] is p:
+                return hit[0]
             t = _as_f64_tensor(p, device=dev, keep_grad=True).reshape(-1, width)
             if t.shape[0] == 1 and B > 1:
                 t = t.expand(B, width)
             cols.append(t)
-            col_of[key] = n_cols
+            # the keyed object is kept alive next to its offset: matrices derived on the fly (from_operation(op).matrix())
+            # are temporaries, and CPython may hand a later temporary the id of a freed one
+            col_of[key] = (n_cols, p)
             n_cols += width
-            return col_of[key]
+            return col_of[key][0]
 
         def flush():
             nonlocal gates, cols, col_of, consts, n_cols
@@ -570,21 +576,33 @@ class NonInteractingFermionicDevice:
             t = self._bits_cache[key] = torch.as_tensor(arr, device=self.torch_device)
         return t
 
+    def _floor2(self, k: int) -> float:
+        """The reference's EPSILON in units of the returned probability: LookupTableStrategy (basis-state inputs unless
+        prob_strategy="ProductState") takes sqrt(|det obs| + eps) with det obs = p^2; ProductStateProbabilityStrategy
+        takes 2^-k sqrt(|det| + eps) (lookup_table_strategy.py:70-71, product_state_strategy.py:211-212; dispatch
+        order nif_device.py:232-237)."""
+        eps = self.pfaffian_epsilon
+        if eps <= 0.0:
+            return 0.0
+        lookup = self.prob_strategy != "ProductState" and self._is_basis_input()
+        return eps if lookup else eps * 4.0 ** (-k)
+
     def _probs_device(self, target: np.ndarray, wire_idx: np.ndarray) -> torch.Tensor:
         """(B, Q) probabilities for outcomes ``target`` (Q, k) measured on shared wire indices (k,)."""
         n = self.num_wires
         k = target.shape[1]
+        floor2 = self._floor2(k)
         segments, B = self._compile()
         full_register = k == n and np.array_equal(wire_idx, np.arange(n))
         if (full_register and target.shape[0] == 1 and self._is_basis_input() and len(segments) == 1
                 and segments[0][0] == "gates" and n <= self.FUSED_MAX_QUBITS):
             bits = self._bits_device(self._state_prep_op.basis_state_bits())
             tgt = self._bits_device(target[0])
-            return _ops.circuit_expval_projector(segments[0][1], segments[0][2], bits, tgt)[:, None]
+            return _ops.circuit_expval_projector(segments[0][1], segments[0][2], bits, tgt, floor2=floor2)[:, None]
         maj = np.stack([2 * wire_idx, 2 * wire_idx + 1], axis=1).ravel()
         cov = self._cov_device(maj)
         outcomes = torch.as_tensor(np.ascontiguousarray(target.astype(np.int8)), device=self.torch_device)
-        return _ops.probs(cov, outcomes)
+        return _ops.probs(cov, outcomes, floor2=floor2)
 
     def get_states_probability(self, target_binary_states, wires=None, **kwargs):
         """Scalar / (B,) for one outcome ``(k,)``; ``(Bq,)`` / ``(Bq, B)`` for a batch ``(Bq, k)`` (:742-810)."""
@@ -650,7 +668,7 @@ class NonInteractingFermionicDevice:
         maj = np.stack([2 * widx, 2 * widx + 1], axis=1).ravel()
         self._compile()
         cov = self._cov_device(maj)
-        p = _ops.probs_all(cov, normalize=True)
+        p = _ops.probs_all(cov, normalize=True, floor2=self._floor2(k))
         batched = self._batched or self._state_prep_op.batch_size is not None
         return self._out(p if batched else p[0])
 

@@ -68,6 +68,59 @@ def folded_row_blocks(n: int, parts: int) -> List[Tuple[Tuple[int, int], Tuple[i
     return out
 
 
+def folded_rows_in_place(compute_rows: Callable[[int, int, torch.Tensor], None], n: int, n_cols: int,
+                         dtype: torch.dtype, device, timeline: Optional[list] = None) -> torch.Tensor:
+    """Triangular square Gram over the ranks WITHOUT staging copies: every rank computes its top and bottom row block
+    directly into the rows of the final (n, n_cols) matrix (``compute_rows(begin, end, out_rows)``), then two
+    all-gathers assemble it -- the top halves in place (ascending rows with ascending rank: slot ``rank`` of the
+    output IS the input), the bottom halves (descending rows with ascending rank) with the row-block views of the
+    final matrix as the output list.  Needs n divisible by 2 * world_size (equal blocks); the caller falls back to
+    :func:`sharded_folded_rows` otherwise."""
+    import torch.distributed as dist
+
+    rank, ws = world()
+    h = n // (2 * ws)
+    assert n == 2 * ws * h and ws > 1
+    (t0, t1), (b0, b1) = folded_row_blocks(n, ws)[rank]
+    assert (t0, t1) == (rank * h, (rank + 1) * h) and (b0, b1) == (n - (rank + 1) * h, n - rank * h)
+    k = torch.empty((n, n_cols), dtype=dtype, device=device)
+    mark = (lambda name: timeline.append((name, _event()))) if timeline is not None else (lambda name: None)
+    mark("begin")
+    compute_rows(t0, t1, k[t0:t1])
+    mark("top_rows")
+    compute_rows(b0, b1, k[b0:b1])
+    mark("bottom_rows")
+    dist.all_gather_into_tensor(k[: n // 2], k[t0:t1])                      # in place: slot `rank` is the input
+    dist.all_gather([k[n - (r + 1) * h: n - r * h] for r in range(ws)], k[b0:b1])
+    mark("all_gather")
+    return k
+
+
+def _event():
+    e = torch.cuda.Event(enable_timing=True) if torch.cuda.is_available() else None
+    if e is not None:
+        e.record()
+    return e
+
+
+def gather_row_ranges(k: torch.Tensor, ranges: List[Tuple[int, int]]) -> torch.Tensor:
+    """``k`` is the full (n_rows, ...) matrix in which this rank has filled rows ranges[rank]; fill in everybody
+    else's rows.  NCCL: one all-gather whose outputs are the row-block views of ``k`` (unequal block sizes are fine);
+    gloo (CPU tests) needs equal sizes, so the blocks are padded there."""
+    import torch.distributed as dist
+
+    rank, ws = world()
+    if ws == 1:
+        return k
+    s, e = ranges[rank]
+    if dist.get_backend() == "nccl":
+        dist.all_gather([k[a:b] for a, b in ranges], k[s:e])
+        return k
+    full = all_gather_rows(k[s:e], ranges, k.shape[0])
+    k.copy_(full)
+    return k
+
+
 def sharded_folded_rows(compute_rows: Callable[[int, int], torch.Tensor], n: int) -> torch.Tensor:
     """Triangular square Gram over the ranks: each rank computes its two row blocks (``compute_rows(begin, end)`` ->
     (end - begin, n) tensor), ONE equal-size all-gather assembles the (n, n) result."""

@@ -54,6 +54,14 @@ class NIFKernel(Kernel):
         #: Gram factorises into 2-qubit factors (csrc/gram_blocks.cu); False forces the dense Pfaffian path
         self.use_block_factorisation = True
         self._blocks_train = None
+        #: optional list that receives (stage, cuda event) pairs of the multi-GPU Gram build (bench / profiling)
+        self.timeline = None
+        #: several ranks: every rank evolves only its slice of the samples and the covariances are all-gathered;
+        #: False = every rank evolves all samples (no collective before the Gram kernel)
+        self.shard_precompute = True
+        #: EPSILON of the reference's magnitude Pfaffian: its Gram entries are sqrt(K^2 + 1e-32) (each cell is a
+        #: LookupTableStrategy probability, nif_kernel.py:210-221 -> lookup_table_strategy.py:70-71); 0 = exact |Pf|
+        self.pfaffian_epsilon = 1e-32
 
     # sklearn's get_params reads attributes named like the __init__ arguments
     @property
@@ -120,12 +128,24 @@ class NIFKernel(Kernel):
         cells of a rank need all of them)."""
         rank, ws = dist_mod.world()
         n = len(x)
-        if ws == 1 or n < 4 * ws or self._differentiating():
+        if ws == 1 or n < 4 * ws or self._differentiating() or not self.shard_precompute:
             return _ops.cov_basis(self._x_to_sptm(x), self._n_qubits)
         ranges = dist_mod.even_ranges(n, ws)
         s, e = ranges[rank]
-        local = _ops.cov_basis(self._x_to_sptm(x[s:e]), self._n_qubits)
-        return dist_mod.all_gather_rows(local, ranges, n)
+        d = 2 * self._n_qubits
+        cov = torch.empty((n, d, d), dtype=torch.float64, device="cuda")
+        _ops.cov_basis(self._x_to_sptm(x[s:e]), self._n_qubits, out=cov[s:e])   # straight into the final rows
+        if self.timeline is not None:
+            self.timeline.append(("cov_local", dist_mod._event()))
+        if n % ws == 0:
+            import torch.distributed as dist
+
+            dist.all_gather_into_tensor(cov, cov[s:e])                          # in place: slot `rank` is the input
+        else:
+            dist_mod.gather_row_ranges(cov, ranges)
+        if self.timeline is not None:
+            self.timeline.append(("cov_all_gather", dist_mod._event()))
+        return cov
 
     @property
     def sptms_train(self) -> torch.Tensor:
@@ -161,7 +181,8 @@ class NIFKernel(Kernel):
             # kernel alignment (kernel.py:200-283): K1 -> K2 -> Pfaffian through the ops that have adjoint kernels
             cov0 = self._x_to_cov(x0)
             cov1 = cov0 if same else self._x_to_cov(x1)
-            k = _ops.gram(cov0, cov1, 2.0 ** (-self._n_qubits), mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE)
+            k = _ops.gram(cov0, cov1, 2.0 ** (-self._n_qubits), mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE,
+                          floor2=self.pfaffian_epsilon)
             return k.to(self.R_DTYPE)
         if self.use_block_factorisation and self._block_plan() is not None:
             b0 = self._x_to_blocks(x0)
@@ -172,7 +193,9 @@ class NIFKernel(Kernel):
                 b1 = self._blocks_train[1]
             else:
                 b1 = b0 if same else self._x_to_blocks(x1)
-            k = self.gram_from_blocks(b0, b1, full=full)
+            k = self.gram_from_blocks(b0, b1, full=full, gather=kwargs.get("gather", True))
+            if isinstance(k, tuple):  # row-sharded: (local rows, (begin, end))
+                return (k[0].to(torch.float32) if self.float32_gram else k[0]).to(self.R_DTYPE), k[1]
             if self.float32_gram:
                 k = k.to(torch.float32)
             return k.to(self.R_DTYPE)
@@ -181,49 +204,86 @@ class NIFKernel(Kernel):
             cov1 = self.covs_train
         else:
             cov1 = cov0 if same else self._x_to_cov(x1)
-        k = self.gram_from_covariances(cov0, cov1, full=kwargs.get("full_rectangle", False))
+        k = self.gram_from_covariances(cov0, cov1, full=full, gather=kwargs.get("gather", True))
+        if isinstance(k, tuple):
+            return (k[0].to(torch.float32) if self.float32_gram else k[0]).to(self.R_DTYPE), k[1]
         if self.float32_gram:
             k = k.to(torch.float32)
         return k.to(self.R_DTYPE)
 
-    def gram_from_covariances(self, cov0: torch.Tensor, cov1: torch.Tensor, full: bool = False) -> torch.Tensor:
+    def gram_from_covariances(self, cov0: torch.Tensor, cov1: torch.Tensor, full: bool = False,
+                              gather: bool = True) -> torch.Tensor:
         n0, n1 = cov0.shape[0], cov1.shape[0]
         scale = 2.0 ** (-self._n_qubits)
         rank, ws = dist_mod.world()
         if ws == 1:
-            return _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE)
-        def rows(s, e):
-            out = torch.zeros((n0, n1), dtype=torch.float64, device=cov0.device)
-            _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_TRIANGLE, row_range=(s, e), out=out)
-            return out[s:e]
+            return _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE,
+                             floor2=self.pfaffian_epsilon)
 
-        if n0 == n1 and not full:
-            # square triangle: folded row blocks = equal rows AND equal cells per rank, no padding in the all-gather
-            return _ops.gram_symmetrize(dist_mod.sharded_folded_rows(rows, n0))
-        ranges = dist_mod.balanced_row_ranges(n0, n1, ws, full=full)
-        k = dist_mod.sharded_rows(rows, ranges, n0)
-        return k if full else _ops.gram_symmetrize(k)
+        def rows(s, e, out_rows):
+            _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_TRIANGLE, row_range=(s, e),
+                      out=out_rows, rows_only=True, floor2=self.pfaffian_epsilon)
 
-    def gram_from_blocks(self, b0: torch.Tensor, b1: torch.Tensor, full: bool = False) -> torch.Tensor:
+        return self._sharded_gram(rows, n0, n1, full, cov0.device, gather)
+
+    def gram_from_blocks(self, b0: torch.Tensor, b1: torch.Tensor, full: bool = False,
+                         gather: bool = True) -> torch.Tensor:
         """Same contract as :meth:`gram_from_covariances` for block-diagonal covariances given as (n, C, 6)."""
         n0, n1 = b0.shape[0], b1.shape[0]
         rank, ws = dist_mod.world()
         if ws == 1:
-            return _ops.gram_blocks4(b0, b1, mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE)
-        def rows(s, e):
-            out = torch.zeros((n0, n1), dtype=torch.float64, device=b0.device)
-            _ops.gram_blocks4(b0, b1, mode=_ops.GRAM_FULL if full else _ops.GRAM_TRIANGLE, row_range=(s, e), out=out)
-            return out[s:e]
+            return _ops.gram_blocks4(b0, b1, mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE,
+                                     floor2=self.pfaffian_epsilon)
 
-        if n0 == n1 and not full:
-            return _ops.gram_symmetrize(dist_mod.sharded_folded_rows(rows, n0))
+        def rows(s, e, out_rows):
+            _ops.gram_blocks4(b0, b1, mode=_ops.GRAM_FULL if full else _ops.GRAM_TRIANGLE, row_range=(s, e),
+                              out=out_rows, rows_only=True, floor2=self.pfaffian_epsilon)
+
+        return self._sharded_gram(rows, n0, n1, full, b0.device, gather)
+
+    def _sharded_gram(self, rows, n0: int, n1: int, full: bool, device, gather: bool = True):
+        """Row-sharded Gram build.  ``rows(begin, end, out_rows)`` launches the Gram kernel for rows
+        [begin, end) writing straight into ``out_rows`` = those rows of the final matrix: no (n0, n1) staging buffer,
+        no zero fill, no pad / permute copies -- the only traffic besides the kernel's own stores is the all-gather
+        and the mirror pass.  ``gather=False`` keeps the result row-sharded and returns ``(local_rows, (begin, end))``
+        (Nystroem.transform applies the normalisation per rank and gathers only on request)."""
+        rank, ws = dist_mod.world()
+        tl = self.timeline
+        if n0 == n1 and not full and gather:
+            if n0 % (2 * ws) == 0:
+                k = dist_mod.folded_rows_in_place(rows, n0, n1, torch.float64, device, timeline=tl)
+            else:
+                def rows_alloc(s, e):
+                    out = torch.empty((e - s, n1), dtype=torch.float64, device=device)
+                    rows(s, e, out)
+                    return out
+
+                k = dist_mod.sharded_folded_rows(rows_alloc, n0)
+            k = _ops.gram_symmetrize(k)
+            if tl is not None:
+                tl.append(("symmetrize", dist_mod._event()))
+            return k
         ranges = dist_mod.balanced_row_ranges(n0, n1, ws, full=full)
-        k = dist_mod.sharded_rows(rows, ranges, n0)
-        return k if full else _ops.gram_symmetrize(k)
+        s, e = ranges[rank]
+        q = min(n0, n1)
+        # the mirror / unit-diagonal pass touches the leading q x q block only; row-sharded output is possible when
+        # that block lies inside ONE rank's rows (always true for the Nystroem transform, n0 >> n1)
+        if not gather and (full or (n0 >= n1 and ranges[0][1] >= q)):
+            local = torch.empty((e - s, n1), dtype=torch.float64, device=device)
+            rows(s, e, local)
+            if not full and s == 0 and e > 0:
+                _ops.gram_symmetrize(local[:q, :q])
+            return local, (s, e)
+        k = torch.empty((n0, n1), dtype=torch.float64, device=device)
+        rows(s, e, k[s:e])
+        dist_mod.gather_row_ranges(k, ranges)
+        k = k if full else _ops.gram_symmetrize(k)
+        return k if gather else (k[s:e], (s, e))
 
     def _compute_similarities_func(self, indices, sptm0, sptm1, p_bar=None):
         """Expectation values for explicit index pairs (nif_kernel.py:210-221), float64, on the GPU."""
         idx = torch.as_tensor(np.asarray(indices), device=sptm0.device)
         c0 = _ops.cov_basis(sptm0[idx[:, 0]].contiguous(), self._n_qubits)
         c1 = _ops.cov_basis(sptm1[idx[:, 1]].contiguous(), self._n_qubits)
-        return _ops.pfaffian(c0 + c1, signed=False, scale=2.0 ** (-self._n_qubits))
+        scale = 2.0 ** (-self._n_qubits)
+        return _ops.pfaffian(c0 + c1, signed=False, scale=scale, epsilon=self.pfaffian_epsilon / (scale * scale))

@@ -43,13 +43,31 @@ class Nystroem(sk_Nystroem):
         self._n_features_out = n_components
         return self
 
+    def _norm_on(self, device) -> torch.Tensor:
+        norm = getattr(self, "_normalization_dev", None)
+        if norm is None or norm.device != device:                     # e.g. after unpickling / sklearn.clone
+            norm = self._normalization_dev = torch.as_tensor(self.normalization_, dtype=torch.float64, device=device)
+        return norm
+
     def transform(self, X):
         check_is_fitted(self)
         embedded = _to_device(self.kernel(X, self.components_))
-        norm = getattr(self, "_normalization_dev", None)
-        if norm is None or norm.device != embedded.device:            # e.g. after unpickling / sklearn.clone
-            norm = self._normalization_dev = torch.as_tensor(self.normalization_, dtype=torch.float64, device=embedded.device)
-        return (embedded @ norm.T).cpu().numpy()                      # nystroem.py:123
+        return (embedded @ self._norm_on(embedded.device).T).cpu().numpy()   # nystroem.py:123
+
+    def transform_sharded(self, X):
+        """Multi-GPU transform that never assembles ``K(X, landmarks)``: every rank builds its row block of the
+        rectangular Gram, applies ``@ normalization_.T`` to it on its own device and returns
+        ``(embedding_rows (CUDA float64), (row_begin, row_end))`` -- the all-gather of the (n, n_components) matrix is
+        left to the caller ("leave sharded and all-gather only if the caller needs it on one device").
+        Single process: the whole embedding with range (0, n)."""
+        check_is_fitted(self)
+        res = self.kernel(X, self.components_, gather=False)
+        if isinstance(res, tuple):
+            local, rng = res
+        else:
+            local, rng = res, (0, len(X))
+        local = _to_device(local)
+        return local @ self._norm_on(local.device).T, rng
 
     def freeze(self):
         self.kernel.freeze()

@@ -41,6 +41,23 @@ def _f64(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+class _Floor:
+    """``with _Floor(floor2):`` -- magnitude floor of the launches inside the block (include/mcb200.h:
+    mcb200_set_abs_floor; the option is per thread and always restored to 0 = off)."""
+
+    def __init__(self, floor2: float):
+        self.floor2 = float(floor2)
+
+    def __enter__(self):
+        if self.floor2 != 0.0:
+            check(_lib.load().mcb200_set_abs_floor(self.floor2))
+
+    def __exit__(self, *exc):
+        if self.floor2 != 0.0:
+            _lib.load().mcb200_set_abs_floor(0.0)
+        return False
+
+
 def _workspace(nbytes: int, device) -> Optional[torch.Tensor]:
     if nbytes <= 0:
         return None
@@ -146,22 +163,23 @@ def circuit_columns(circ: CompiledCircuit, params: torch.Tensor, cols: Optional[
 
 
 def circuit_expval_projector(circ: CompiledCircuit, params: torch.Tensor, init_bits: Optional[torch.Tensor] = None,
-                             target_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """<y|rho_b|y> on all wires, one fused kernel (B,)."""
+                             target_bits: Optional[torch.Tensor] = None, floor2: float = 0.0) -> torch.Tensor:
+    """<y|rho_b|y> on all wires, one fused kernel (B,).  ``floor2`` > 0: sqrt(p^2 + floor2), see :func:`probs`."""
     if _ag.needs_grad(params):  # differentiable route: K1 -> K2 -> K3 as separate ops, each with its adjoint kernel
         n = circ.n_qubits
         dev = params.device
         cov = cov_basis(circuit_columns(circ, params), n, init_bits)
         tgt = torch.zeros((1, n), dtype=torch.int8, device=dev) if target_bits is None else \
             target_bits.to(device=dev, dtype=torch.int8).reshape(1, n)
-        return probs(cov, tgt)[:, 0]
+        return probs(cov, tgt, floor2=floor2)[:, 0]
     params = circ._params(params)
     B = params.shape[0]
     bits = lambda t: None if t is None else t.to(device=params.device, dtype=torch.int8).contiguous()
     ib, tb = bits(init_bits), bits(target_bits)
     out = torch.empty((B,), dtype=torch.float64, device=params.device)
-    check(_lib.load().mcb200_circuit_expval_projector(C.byref(circ._struct), _ptr(params), B, _ptr(ib), _ptr(tb),
-                                                      _ptr(out), _stream()))
+    with _Floor(floor2):
+        check(_lib.load().mcb200_circuit_expval_projector(C.byref(circ._struct), _ptr(params), B, _ptr(ib), _ptr(tb),
+                                                          _ptr(out), _stream()))
     return out
 
 
@@ -218,8 +236,9 @@ def product_state_cov(amplitudes: torch.Tensor, extended: bool = False) -> torch
 
 
 # ------------------------------------------------------------------------------------------------ covariance
-def cov_basis(x: torch.Tensor, n_qubits: int, bits: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """cov[b] = X_b^T Lambda_0(bits) X_b for X (B, d, m)."""
+def cov_basis(x: torch.Tensor, n_qubits: int, bits: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """cov[b] = X_b^T Lambda_0(bits) X_b for X (B, d, m); ``out`` (B, m, m) contiguous float64 receives the result."""
     if _ag.needs_grad(x):
         return _ag.CovBasis.apply(x, n_qubits, bits)
     x = _f64(x, "x")
@@ -227,7 +246,10 @@ def cov_basis(x: torch.Tensor, n_qubits: int, bits: Optional[torch.Tensor] = Non
     if d != 2 * n_qubits:
         raise ValueError("x must have 2*n_qubits rows")
     ib = None if bits is None else bits.to(device=x.device, dtype=torch.int8).contiguous()
-    out = torch.empty((B, m, m), dtype=torch.float64, device=x.device)
+    if out is None:
+        out = torch.empty((B, m, m), dtype=torch.float64, device=x.device)
+    elif out.shape != (B, m, m) or out.dtype != torch.float64 or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous float64 ({B}, {m}, {m}) tensor")
     check(_lib.load().mcb200_cov_basis(_ptr(x), _ptr(ib), B, n_qubits, m, _ptr(out), _stream()))
     return out
 
@@ -262,10 +284,19 @@ def cov_dense(r: torch.Tensor, l0: torch.Tensor, idx: Optional[torch.Tensor] = N
 
 
 # ------------------------------------------------------------------------------------------------ Pfaffians
-def pfaffian(a: torch.Tensor, signed: bool = False, scale: float = 1.0) -> torch.Tensor:
-    """Batched Pfaffian of real skew-symmetric matrices (..., m, m) -> (...)."""
+def _apply_floor(v: torch.Tensor, floor2: float) -> torch.Tensor:
+    """Differentiable restatement of the in-kernel floor for the autograd routes."""
+    return torch.sqrt(v * v + floor2) if floor2 > 0.0 else v
+
+
+def pfaffian(a: torch.Tensor, signed: bool = False, scale: float = 1.0, epsilon: float = 0.0) -> torch.Tensor:
+    """Batched Pfaffian of real skew-symmetric matrices (..., m, m) -> (...).
+
+    ``epsilon`` > 0 (magnitude mode only): ``scale * sqrt(Pf^2 + epsilon)``, the value of the reference's
+    ``utils.pfaffian(sign=False, epsilon=...)`` = ``sqrt(|det A| + EPSILON)`` (utils/_pfaffian.py:110-118)."""
+    eps = 0.0 if signed else float(epsilon)
     if _ag.needs_grad(a):
-        return _ag.Pfaffian.apply(a, signed, scale)
+        return _apply_floor(_ag.Pfaffian.apply(a, signed, scale), scale * scale * eps)
     a = _f64(a, "a")
     m = a.shape[-1]
     if a.shape[-2] != m:
@@ -275,15 +306,20 @@ def pfaffian(a: torch.Tensor, signed: bool = False, scale: float = 1.0) -> torch
     out = torch.empty((n,), dtype=torch.float64, device=a.device)
     lib = _lib.load()
     ws = _workspace(lib.mcb200_pfaffian_workspace_bytes(n, m), a.device)
-    check(lib.mcb200_pfaffian(_ptr(a), n, m, PF_SIGNED if signed else PF_ABS, float(scale), _ptr(out), _ptr(ws),
-                              _stream()))
+    with _Floor(scale * scale * eps):
+        check(lib.mcb200_pfaffian(_ptr(a), n, m, PF_SIGNED if signed else PF_ABS, float(scale), _ptr(out), _ptr(ws),
+                                  _stream()))
     return out.reshape(batch_shape)
 
 
-def probs(cov: torch.Tensor, outcomes: torch.Tensor, normalize: bool = False) -> torch.Tensor:
-    """out[b, q] = 2^-k |Pf(cov[b] + Lambda_y(outcomes[q]))|; cov (B, 2k, 2k), outcomes (Q, k)."""
+def probs(cov: torch.Tensor, outcomes: torch.Tensor, normalize: bool = False, floor2: float = 0.0) -> torch.Tensor:
+    """out[b, q] = 2^-k |Pf(cov[b] + Lambda_y(outcomes[q]))|; cov (B, 2k, 2k), outcomes (Q, k).
+
+    ``floor2`` > 0 returns sqrt(p^2 + floor2) (before the optional normalisation): the reference's probabilities are
+    ``sqrt(|det| + 1e-32)`` -- floor2 = 1e-32 for LookupTableStrategy (lookup_table_strategy.py:70-71), 4^-k 1e-32 for
+    ProductStateProbabilityStrategy (product_state_strategy.py:211-212)."""
     if _ag.needs_grad(cov):
-        p = _ag.Probs.apply(cov, outcomes)
+        p = _apply_floor(_ag.Probs.apply(cov, outcomes), floor2)
         return p / p.sum(dim=1, keepdim=True) if normalize else p
     cov = _f64(cov, "cov")
     outcomes = outcomes.to(device=cov.device, dtype=torch.int8).contiguous()
@@ -301,20 +337,21 @@ def probs(cov: torch.Tensor, outcomes: torch.Tensor, normalize: bool = False) ->
             mat = cov.clone()
             mat[:, ev, ev + 1] += sgn[q]
             mat[:, ev + 1, ev] -= sgn[q]
-            out[:, q] = pfaffian(mat, signed=False, scale=2.0 ** -k)
+            out[:, q] = pfaffian(mat, signed=False, scale=2.0 ** -k, epsilon=floor2 * 4.0 ** k)
         return out / out.sum(dim=1, keepdim=True) if normalize else out
     out = torch.empty((B, Q), dtype=torch.float64, device=cov.device)
-    check(_lib.load().mcb200_probs(_ptr(cov), _ptr(outcomes), B, Q, k, int(normalize), _ptr(out), _stream()))
+    with _Floor(floor2):
+        check(_lib.load().mcb200_probs(_ptr(cov), _ptr(outcomes), B, Q, k, int(normalize), _ptr(out), _stream()))
     return out
 
 
-def probs_all(cov: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+def probs_all(cov: torch.Tensor, normalize: bool = False, floor2: float = 0.0) -> torch.Tensor:
     """Every outcome of the k measured wires: out[b, q] for q in range(2^k), MSB first; cov (B, 2k, 2k)."""
     if _ag.needs_grad(cov):  # the elimination tree has no adjoint; enumerate the outcomes (states_to_binary order)
         k = cov.shape[-1] // 2
         q = torch.arange(1 << k, device=cov.device)
         outcomes = ((q[:, None] >> torch.arange(k - 1, -1, -1, device=cov.device)[None, :]) & 1).to(torch.int8)
-        return probs(cov, outcomes, normalize)
+        return probs(cov, outcomes, normalize, floor2=floor2)
     cov = _f64(cov, "cov")
     B, m, _ = cov.shape
     k = m // 2
@@ -323,7 +360,8 @@ def probs_all(cov: torch.Tensor, normalize: bool = False) -> torch.Tensor:
     out = torch.empty((B, 1 << k), dtype=torch.float64, device=cov.device)
     lib = _lib.load()
     ws = _workspace(lib.mcb200_probs_all_workspace_bytes(k), cov.device)
-    check(lib.mcb200_probs_all(_ptr(cov), B, k, int(normalize), _ptr(out), _ptr(ws), _stream()))
+    with _Floor(floor2):
+        check(lib.mcb200_probs_all(_ptr(cov), B, k, int(normalize), _ptr(out), _ptr(ws), _stream()))
     return out
 
 
@@ -402,7 +440,7 @@ def pauli_sum_small(cov: torch.Tensor, term_ptr: torch.Tensor, indices: torch.Te
 
 
 # ------------------------------------------------------------------------------------------------ Gram
-def _gram_differentiable(cov0, cov1, scale, mode, row_range):
+def _gram_differentiable(cov0, cov1, scale, mode, row_range, floor2=0.0):
     """Training-size Gram under autograd (kernel alignment, ml/kernels/kernel.py:200-283): the evaluated cells are
     batched Pfaffians of cov0[i] + cov1[j] through the differentiable Pfaffian op; cell selection, mirroring and the
     unit diagonal follow gram_matrix.py:127-161,191-195."""
@@ -415,7 +453,7 @@ def _gram_differentiable(cov0, cov1, scale, mode, row_range):
     else:
         keep = (jj > ii) if n0 < n1 else (ii > jj)
     ii, jj = ii[keep], jj[keep]
-    vals = pfaffian(cov0[ii] + cov1[jj], signed=False, scale=scale)
+    vals = _apply_floor(pfaffian(cov0[ii] + cov1[jj], signed=False, scale=scale), floor2)
     K = torch.zeros((n0, n1), dtype=torch.float64, device=dev).index_put((ii, jj), vals)
     if mode == GRAM_REFERENCE:
         q = min(n0, n1)
@@ -427,23 +465,45 @@ def _gram_differentiable(cov0, cov1, scale, mode, row_range):
     return K
 
 
+def _gram_out(out: Optional[torch.Tensor], n0: int, n1: int, rb: int, re: int, rows_only: bool, device):
+    """Output buffer of a Gram launch and the pointer the kernel sees as ``K`` (row 0 of the FULL matrix).
+
+    ``rows_only``: ``out`` holds just the rows [rb, re) -- shape (re - rb, n1), e.g. a view into the final matrix of a
+    row-sharded build; the kernel only writes ``K[i * ldk + j]`` for rb <= i < re (mode TRIANGLE / FULL), so ``K`` is
+    the buffer shifted back by ``rb`` rows and nothing of size (n0, n1) is ever allocated or zero-filled."""
+    if rows_only:
+        if out is None:
+            out = torch.empty((re - rb, n1), dtype=torch.float64, device=device)
+        if out.shape != (re - rb, n1) or out.dtype != torch.float64 or out.stride(1) != 1:
+            raise ValueError(f"rows-only Gram buffer must be float64 ({re - rb}, {n1}) with unit column stride")
+        return out, out.data_ptr() - rb * out.stride(0) * 8 if re > rb else out.data_ptr()
+    if out is None:
+        out = torch.zeros((n0, n1), dtype=torch.float64, device=device)
+    return out, out.data_ptr()
+
+
 def gram(cov0: torch.Tensor, cov1: torch.Tensor, scale: float, mode: int = GRAM_REFERENCE,
-         row_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """K[i, j] = scale |Pf(cov0[i] + cov1[j])| with the reference's triangle/mirror/unit-diagonal rules."""
+         row_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
+         rows_only: bool = False, floor2: float = 0.0) -> torch.Tensor:
+    """K[i, j] = scale |Pf(cov0[i] + cov1[j])| with the reference's triangle/mirror/unit-diagonal rules.
+    ``floor2`` > 0: evaluated entries are sqrt(K^2 + floor2) (the reference's Gram goes through LookupTableStrategy,
+    i.e. sqrt(|det| + 1e-32), nif_kernel.py:210-221 -> lookup_table_strategy.py:70-71)."""
     if _ag.needs_grad(cov0, cov1):
-        return _gram_differentiable(cov0, cov1, scale, mode, row_range)
+        return _gram_differentiable(cov0, cov1, scale, mode, row_range, floor2)
     cov0, cov1 = _f64(cov0, "cov0"), _f64(cov1, "cov1")
     n0, d, _ = cov0.shape
     n1 = cov1.shape[0]
     if cov1.shape[1:] != (d, d):
         raise ValueError("cov0 and cov1 must hold matrices of the same size")
     rb, re = (0, n0) if row_range is None else row_range
-    if out is None:
-        out = torch.zeros((n0, n1), dtype=torch.float64, device=cov0.device)
+    if rows_only and mode == GRAM_REFERENCE:
+        raise ValueError("rows_only needs mode TRIANGLE or FULL (REFERENCE mirrors into rows outside the block)")
+    out, kptr = _gram_out(out, n0, n1, rb, re, rows_only, cov0.device)
     lib = _lib.load()
     ws = _workspace(lib.mcb200_gram_workspace_bytes(n0, n1, d), cov0.device)
-    check(lib.mcb200_gram(_ptr(cov0), _ptr(cov1), n0, n1, d, rb, re, mode, float(scale), _ptr(out), out.stride(0),
-                          _ptr(ws), _stream()))
+    with _Floor(floor2):
+        check(lib.mcb200_gram(_ptr(cov0), _ptr(cov1), n0, n1, d, rb, re, mode, float(scale), kptr, out.stride(0),
+                              _ptr(ws), _stream()))
     return out
 
 
@@ -461,7 +521,8 @@ def circuit_pair_blocks(circ: CompiledCircuit, params: torch.Tensor, pair_wire0:
 
 
 def gram_blocks4(blocks0: torch.Tensor, blocks1: torch.Tensor, mode: int = GRAM_REFERENCE,
-                 row_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 row_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
+                 rows_only: bool = False, floor2: float = 0.0) -> torch.Tensor:
     """Gram of block-diagonal covariances: blocks (n, C, 6) = upper triangles of the C 4x4 diagonal blocks."""
     blocks0, blocks1 = _f64(blocks0, "blocks0"), _f64(blocks1, "blocks1")
     n0, C, six = blocks0.shape
@@ -469,10 +530,12 @@ def gram_blocks4(blocks0: torch.Tensor, blocks1: torch.Tensor, mode: int = GRAM_
     if six != 6 or blocks1.shape[1:] != (C, 6):
         raise ValueError("blocks must be (n, C, 6)")
     rb, re = (0, n0) if row_range is None else row_range
-    if out is None:
-        out = torch.zeros((n0, n1), dtype=torch.float64, device=blocks0.device)
-    check(_lib.load().mcb200_gram_blocks4(_ptr(blocks0), _ptr(blocks1), n0, n1, C, rb, re, mode, 2.0 ** (-2 * C),
-                                          _ptr(out), out.stride(0), _stream()))
+    if rows_only and mode == GRAM_REFERENCE:
+        raise ValueError("rows_only needs mode TRIANGLE or FULL (REFERENCE mirrors into rows outside the block)")
+    out, kptr = _gram_out(out, n0, n1, rb, re, rows_only, blocks0.device)
+    with _Floor(floor2):
+        check(_lib.load().mcb200_gram_blocks4(_ptr(blocks0), _ptr(blocks1), n0, n1, C, rb, re, mode, 2.0 ** (-2 * C),
+                                              kptr, out.stride(0), _stream()))
     return out
 
 

@@ -43,10 +43,12 @@ def _like(result: torch.Tensor, ref):
 def pfaffian(matrix, sign: bool = False, epsilon: float = 1e-32, dtype: Optional[torch.dtype] = None):
     """Pfaffian of real skew-symmetric matrices ``(..., 2n, 2n)``: signed (``sign=True``) or magnitude.
 
-    ``epsilon`` is accepted for signature compatibility; the magnitude is ``|Pf|`` computed directly (no
-    determinant, hence no floor needed).  Complex inputs contribute their real part (_pfaffian.py:91-95)."""
+    Magnitude mode returns ``sqrt(Pf^2 + epsilon)`` = the reference's ``sqrt(|det A| + EPSILON)`` (PfaffianDet,
+    _pfaffian.py:110-118): ``|Pf|`` comes from the Parlett-Reid kernel and the additive floor is applied in the
+    kernel's epilogue.  ``epsilon=0`` gives ``|Pf|`` itself.  Complex inputs contribute their real part
+    (_pfaffian.py:91-95)."""
     t = _to_device(matrix)
-    return _like(_ops.pfaffian(t, signed=bool(sign)), matrix)
+    return _like(_ops.pfaffian(t, signed=bool(sign), epsilon=0.0 if sign else float(epsilon)), matrix)
 
 
 def signed_pfaffian(matrix, dtype: Optional[torch.dtype] = None):

@@ -250,6 +250,17 @@ def test_utils_pfaffian_namespace():
     a = rng.random((3, 4, 4))
     a = a - np.swapaxes(a, -1, -2)
     np.testing.assert_allclose(utils.pfaffian(a) ** 2, np.abs(np.linalg.det(a)), rtol=1e-10)
+    # epsilon is honoured like the reference's PfaffianDet: sqrt(|det A| + epsilon) (utils/_pfaffian.py:110-118)
+    from oracle import pfaffian as opf
+    tiny = 1e-7 * a
+    for eps in (1e-32, 1e-20, 0.0):
+        np.testing.assert_allclose(utils.pfaffian(tiny, epsilon=eps), opf.pfaffian_det(tiny, eps), rtol=1e-10, atol=0)
+    assert np.all(utils.pfaffian(np.zeros((2, 4, 4))) == 1e-16)          # exact zeros come back as sqrt(1e-32)
+    assert np.all(utils.pfaffian(np.zeros((2, 4, 4)), epsilon=0.0) == 0.0)
+    big = rng.random((2, 70, 70))
+    big = 1e-3 * (big - np.swapaxes(big, -1, -2))                          # block-tile kernel path
+    np.testing.assert_allclose(utils.pfaffian(big, epsilon=1e-120), opf.pfaffian_det(big, 1e-120), rtol=1e-9)
+    np.testing.assert_allclose(utils.pfaffian(big, epsilon=1e-2), opf.pfaffian_det(big, 1e-2), rtol=1e-10)
 
 
 @pytest.mark.parametrize("n,nf,rot,ent", [(8, 8, "X,Z", "fswap"), (6, 5, "Y,Z", "fswap"), (10, 10, "X", "identity"),

@@ -447,6 +447,33 @@ def test_gram_matches_reference_formulation(n, shape):
     mops.gram(dev(c0), dev(c1), scale=2.0 ** -n, mode=mops.GRAM_TRIANGLE, row_range=(0, h), out=tri)
     mops.gram(dev(c0), dev(c1), scale=2.0 ** -n, mode=mops.GRAM_TRIANGLE, row_range=(h, shape[0]), out=tri)
     np.testing.assert_array_equal(mops.gram_symmetrize(tri).cpu().numpy(), out)
+    # the same with rows-only buffers (views into the final matrix; nothing zero-filled) -- what the multi-GPU build does
+    final = torch.full(shape, float("nan"), dtype=torch.float64, device="cuda")
+    mops.gram(dev(c0), dev(c1), scale=2.0 ** -n, mode=mops.GRAM_TRIANGLE, row_range=(0, h), out=final[:h], rows_only=True)
+    mops.gram(dev(c0), dev(c1), scale=2.0 ** -n, mode=mops.GRAM_TRIANGLE, row_range=(h, shape[0]), out=final[h:], rows_only=True)
+    np.testing.assert_array_equal(mops.gram_symmetrize(final).cpu().numpy(), out)
+    with pytest.raises(ValueError):
+        mops.gram(dev(c0), dev(c1), scale=1.0, row_range=(0, h), out=final[:h], rows_only=True)  # REFERENCE mirrors outside
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (33, 33), (70, 45), (45, 70), (200, 97), (64, 64)])
+def test_gram_symmetrize_tiles(shape):
+    """GramMatrix.symmetrize_ / _fill_diagonal_ (gram_matrix.py:127-161) by the tiled transpose kernel."""
+    from matchcake_b200 import ops as mops
+
+    n0, n1 = shape
+    a = np.random.default_rng(n0 * 1000 + n1).random(shape)
+    q = min(n0, n1)
+    ref = a.copy()
+    sq = ref[:q, :q]
+    src = np.tril(sq, -1) if n0 >= n1 else np.triu(sq, 1)               # evaluated triangle (gram_matrix.py:191-195)
+    sq[...] = src + src.T + np.eye(q)
+    # a non-contiguous view (row block of a wider matrix) exercises the leading dimension
+    wide = torch.zeros((n0, n1 + 5), dtype=torch.float64, device="cuda")
+    wide[:, :n1] = dev(a)
+    got = mops.gram_symmetrize(wide[:, :n1])
+    np.testing.assert_array_equal(got.cpu().numpy(), ref)
+    assert float(wide[:, n1:].abs().max()) == 0.0
 
 
 def test_gram_identical_rows_is_all_ones():

@@ -207,6 +207,21 @@ for n in (2, 7, 10, 33):
     sq = torch.arange(n * n, dtype=torch.float64).reshape(n, n)
     got = dm.sharded_folded_rows(lambda s, e: sq[s:e].clone(), n)
     assert torch.equal(got, sq), (n, got)
+# in-place folded gather: both halves land in their final rows (top over WORLD, bottom over the reversed group)
+for n in (4, 8, 32):
+    sq = torch.arange(n * n, dtype=torch.float64).reshape(n, n)
+    def rows(s, e, out):
+        out.copy_(sq[s:e])
+    got = dm.folded_rows_in_place(rows, n, n, torch.float64, "cpu")
+    assert torch.equal(got, sq), (n, got)
+# uneven contiguous row blocks gathered into the final matrix
+for n0, n1 in ((11, 7), (64, 5)):
+    fullm = torch.arange(n0 * n1, dtype=torch.float64).reshape(n0, n1)
+    rr = dm.balanced_row_ranges(n0, n1, 2)
+    k = torch.full((n0, n1), -1.0, dtype=torch.float64)
+    s, e = rr[dist.get_rank()]
+    k[s:e] = fullm[s:e]
+    assert torch.equal(dm.gather_row_ranges(k, rr), fullm)
 dist.barrier(); dist.destroy_process_group()
 print("ok", os.environ["RANK"])
 """
