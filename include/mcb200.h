@@ -194,6 +194,12 @@ int mcb200_circuit_expval_projector(const mcb200_circuit_t* circuit_host, const 
                                     int64_t B, const int8_t* init_bits, const int8_t* target_bits,
                                     double* out, void* stream);
 
+/* Route of mcb200_circuit_expval_projector for <= 32 qubits, sticky per calling thread (tests and benchmarks pin it;
+ * 0 = automatic is the initial value):  1 = column route (X = R[:, :] built gate by gate from the right, then
+ * Lambda = X^T Lambda_0 X on the FP64 tensor pipe: deep circuits),  2 = covariance route (Lambda <- G^T Lambda G gate by
+ * gate, no conjugation: shallow circuits, config C2).  Both replace nif_device.py:168-195 + :1118-1131. */
+int mcb200_set_expval_route(int32_t route);
+
 /* ------------------------------------------------------------------ Gram builder */
 /* K[i, j] = scale * |Pf(cov0[i] + cov1[j])| for rows row_begin <= i < row_end (SURVEY.md A.5:
  * equals P(0..0 | R_i R_j^T) of NIFKernel._compute_similarities_func, nif_kernel.py:210-221).

@@ -42,6 +42,7 @@ SIGNATURES = {
     "mcb200_device_count": (c_i32, []),
     "mcb200_set_abs_floor": (c_i32, [c_f64]),
     "mcb200_get_abs_floor": (c_f64, []),
+    "mcb200_set_expval_route": (c_i32, [c_i32]),
     "mcb200_circuit_columns": (c_i32, [C.POINTER(CircuitStruct), c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]),
     "mcb200_sptm_matmul": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_vp]),
     "mcb200_matchgate_sptm": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
@@ -107,6 +108,11 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(load().mcb200_launch_count())
+
+
+def set_expval_route(route: int) -> None:
+    """0 = automatic, 1 = column route, 2 = covariance route of the fused projector kernel (sticky per thread)."""
+    check(load().mcb200_set_expval_route(int(route)))
 
 
 def reset_launch_count() -> None:

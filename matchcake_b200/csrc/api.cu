@@ -2,12 +2,14 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "tiles_api.cuh"
 
 namespace mcb200 {
 
 thread_local std::string g_last_error;
 std::atomic<long long> g_launch_count{0};
 thread_local double g_abs_floor2 = 0.0;
+thread_local int g_expval_route = 0;
 
 int set_error(const char* fmt, ...) {
   char buf[1024];
@@ -82,6 +84,11 @@ extern "C" int mcb200_set_abs_floor(double floor2) {
   return 0;
 }
 extern "C" double mcb200_get_abs_floor(void) { return g_abs_floor2; }
+extern "C" int mcb200_set_expval_route(int32_t route) {
+  if (route < 0 || route > 2) return set_error("set_expval_route: route must be 0 (auto), 1 (columns) or 2 (covariance)");
+  g_expval_route = route;
+  return 0;
+}
 extern "C" int64_t mcb200_launch_count(void) { return g_launch_count.load(); }
 extern "C" void mcb200_reset_launch_count(void) { g_launch_count.store(0); }
 

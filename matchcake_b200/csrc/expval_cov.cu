@@ -1,0 +1,465 @@
+// Fused projector expectation value, one WARP per circuit instance, covariance (Heisenberg) route, 2N <= 64:
+//   Lambda_0 (basis state)  ->  Lambda <- G^T Lambda G  gate by gate, in APPLICATION order, in shared memory
+//   ->  + Lambda_y  ->  register-tile Pfaffian (pfaffian_tiles.cuh)  ->  2^-N |Pf|.
+// Compared with the column route (expval_warp.cu: X = R, then Lambda = X^T Lambda_0 X as d^3 flop of DMMA) the
+// conjugation never happens: a rotation gate costs 2 x 12 d flop on Lambda (rows, then columns) instead of 12 d on X,
+// so the route wins while  12 d n_rot < d^3,  i.e. for shallow circuits on a full-register projector (config C2:
+// 24 rotation gates, d = 32: 18.4 kflop instead of 9.2 + 32.8).  expval_warp_launch picks the route.
+//
+//  * Everything that does not depend on the circuit INSTANCE is resolved once per block: fSWAPs (adjacent or long
+//    range) only permute a logical -> physical index table, so every gate's four physical rows, the layers of gates on
+//    disjoint rows, the kind pattern of each run of rotations on one wire pair and the de-duplicated list of
+//    parameter columns that need a sincos are tables in shared memory; the instance loop decodes nothing.
+//  * Lambda (32H x 32H, stride 32H + 1: row AND column accesses are bank-conflict free) belongs to the warp.  A layer is
+//    applied as phase 0 (lane = column: rows p0..p3 <- G^T rows) for all its runs, then phase 1 (lane = row: columns
+//    p0..p3 <- columns G).  Left and right factors of disjoint gates commute, so a layer needs two warp barriers.
+//  * sincos is evaluated for a GROUP of instances at a time with (instance, parameter column) pairs spread over
+//    the lanes: config C2 has one parameter pair per instance, so a group of 8 instances costs one pass.
+//  * The Pfaffian reads Lambda through the final permutation straight into DMMA accumulator fragments; its scratch
+//    aliases the (then dead) Lambda buffer.
+// Replaces the QNode execution path of SURVEY.md section 3.1 (devices/nif_device.py:562 -> :281 -> :506 -> :742,
+// lookup_table_strategy.py:19-71, utils/_pfaffian.py:78-119).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "pfaffian_tiles.cuh"
+#include "tiles_api.cuh"
+
+namespace mcb200 {
+
+struct CovCircuit {
+  const mcb200_gate_t* gates;
+  int n_gates, n_qubits, n_param_cols;
+  const double* scale;
+  const double* bias;
+  const double* consts;
+};
+
+// Packed kind pattern of a run of L <= 3 rotations on one wire pair: L | k0 << 2 | k1 << 4 | k2 << 6 (k = gate kind);
+// explicit 4x4 blocks are runs of their own: kPatBlock | const/param << 1 | transposed.
+__host__ __device__ constexpr int cov_pat(int L, int k0, int k1 = 0, int k2 = 0) {
+  return L | (k0 << 2) | (k1 << 4) | (k2 << 6);
+}
+constexpr int kPatBlock = 256;       // + 2 if the block is read from the parameter row, + 1 if transposed
+constexpr int kPatMixedLayer = -1;   // layer whose runs do not share one rotation pattern
+
+// One Givens pair of Lambda <- G^T Lambda (or Lambda G): with G|_(i,j) = [[c, t], [-t, c]] (the X <- G X convention of
+// circuit_dev.cuh) the transposed action is  new_i = c x_i - t x_j,  new_j = c x_j + t x_i.
+__device__ __forceinline__ void cov_givens(double& xi, double& xj, double c, double t) {
+  const double yi = c * xi - t * xj;
+  xj = c * xj + t * xi;
+  xi = yi;
+}
+
+// a = {cos s, sin s}, b = {cos d, sin d}, s = (p0 + p1) / 2, d = (p0 - p1) / 2
+//   RXRX pairs (0,3): (cd, sd), (1,2): (cs, ss)      sptm_comp_rxrx.py:48-57
+//   RYRY pairs (0,2): (cs, -ss), (1,3): (cd, sd)     sptm_comp_ryry.py:53-67
+//   RZRZ pairs (0,1): (cs, ss), (2,3): (cd, sd)      sptm_comp_rzrz.py:51-67
+template <int KIND>
+__device__ __forceinline__ void cov_rotation(double (&x)[4], const double2& a, const double2& b) {
+  if constexpr (KIND == MCB200_GATE_RXRX) {
+    cov_givens(x[0], x[3], b.x, b.y);
+    cov_givens(x[1], x[2], a.x, a.y);
+  } else if constexpr (KIND == MCB200_GATE_RYRY) {
+    cov_givens(x[0], x[2], a.x, -a.y);
+    cov_givens(x[1], x[3], b.x, b.y);
+  } else {
+    cov_givens(x[0], x[1], a.x, a.y);
+    cov_givens(x[2], x[3], b.x, b.y);
+  }
+}
+
+__device__ __forceinline__ void cov_rotation_dyn(int kind, double (&x)[4], const double2& a, const double2& b) {
+  if (kind == MCB200_GATE_RXRX) cov_rotation<MCB200_GATE_RXRX>(x, a, b);
+  else if (kind == MCB200_GATE_RYRY) cov_rotation<MCB200_GATE_RYRY>(x, a, b);
+  else cov_rotation<MCB200_GATE_RZRZ>(x, a, b);
+}
+
+// Shared-memory accessors on 32-bit byte offsets from the block's dynamic shared memory: keeps every address a
+// single 32-bit register (IMAD / IADD + LDS), nothing is re-derived from 64-bit pointers inside the loops.
+struct Smem {
+  unsigned char* base;
+  __device__ __forceinline__ double ld(unsigned off) const { return *reinterpret_cast<const double*>(base + off); }
+  __device__ __forceinline__ double2 ld2(unsigned off) const { return *reinterpret_cast<const double2*>(base + off); }
+  __device__ __forceinline__ void st(unsigned off, double v) const { *reinterpret_cast<double*>(base + off) = v; }
+};
+
+// All runs [rb, re) of one layer share the rotation pattern (L; K0, K1, K2): one phase of the layer.
+//   own    = byte offset of this lane's column (phase 0) / row (phase 1) within Lambda
+//   stride = byte stride of the gate's index: a row (phase 0) or an element (phase 1);  hs: second element (H = 2)
+template <int H, int L, int K0, int K1, int K2>
+__device__ __forceinline__ void cov_layer_uniform(const Smem sm, const int4* sp, const int4* sinf, int rb, int re,
+                                                  unsigned own, unsigned stride, unsigned hs, unsigned trig_i) {
+#pragma unroll 1
+  for (int r = rb; r < re; ++r) {
+    const int4 p = sp[r];
+    const int4 ti = sinf[r];
+    const unsigned a0 = own + p.x * stride, a1 = own + p.y * stride, a2 = own + p.z * stride, a3 = own + p.w * stride;
+    double2 ca[L], cb[L];
+    ca[0] = sm.ld2(trig_i + ti.x);
+    cb[0] = sm.ld2(trig_i + ti.x + 16);
+    if constexpr (L > 1) {
+      ca[1] = sm.ld2(trig_i + ti.y);
+      cb[1] = sm.ld2(trig_i + ti.y + 16);
+    }
+    if constexpr (L > 2) {
+      ca[2] = sm.ld2(trig_i + ti.z);
+      cb[2] = sm.ld2(trig_i + ti.z + 16);
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      double x[4] = {sm.ld(a0 + h * hs), sm.ld(a1 + h * hs), sm.ld(a2 + h * hs), sm.ld(a3 + h * hs)};
+      cov_rotation<K0>(x, ca[0], cb[0]);
+      if constexpr (L > 1) cov_rotation<K1>(x, ca[1], cb[1]);
+      if constexpr (L > 2) cov_rotation<K2>(x, ca[2], cb[2]);
+      sm.st(a0 + h * hs, x[0]);
+      sm.st(a1 + h * hs, x[1]);
+      sm.st(a2 + h * hs, x[2]);
+      sm.st(a3 + h * hs, x[3]);
+    }
+  }
+}
+
+// Layer with mixed patterns (or explicit 4x4 blocks): per-run decode, per-gate branch on the kind.
+template <int H>
+__device__ __forceinline__ void cov_layer_mixed(const Smem sm, const int4* sp, const int4* sinf, int rb, int re,
+                                                unsigned own, unsigned stride, unsigned hs, unsigned trig_i,
+                                                const double* consts, const double* prow) {
+#pragma unroll 1
+  for (int r = rb; r < re; ++r) {
+    const int4 p = sp[r];
+    const int4 ti = sinf[r];
+    const unsigned a[4] = {own + p.x * stride, own + p.y * stride, own + p.z * stride, own + p.w * stride};
+    double x[H][4];
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[h][k] = sm.ld(a[k] + h * hs);
+    if (ti.w >= kPatBlock) {
+      // G|_block = M (or M^T): y_k = sum_b G[b][k] x_b
+      const double* m4 = ((ti.w & 2) ? prow : consts) + ti.x;
+      const bool tr = ti.w & 1;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        double y[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          y[k] = (tr ? m4[4 * k] : m4[k]) * x[h][0] + (tr ? m4[4 * k + 1] : m4[4 + k]) * x[h][1] +
+                 (tr ? m4[4 * k + 2] : m4[8 + k]) * x[h][2] + (tr ? m4[4 * k + 3] : m4[12 + k]) * x[h][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[h][k] = y[k];
+      }
+    } else {
+      const int len = ti.w & 3;
+      const int toff[3] = {ti.x, ti.y, ti.z};
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        if (u < len) {
+          const int kind = (ti.w >> (2 + 2 * u)) & 3;
+          const double2 ca = sm.ld2(trig_i + toff[u]), cb = sm.ld2(trig_i + toff[u] + 16);
+#pragma unroll
+          for (int h = 0; h < H; ++h) cov_rotation_dyn(kind, x[h], ca, cb);
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sm.st(a[k] + h * hs, x[h][k]);
+  }
+}
+
+#define MCB200_COV_U1(k0) \
+  case cov_pat(1, k0): cov_layer_uniform<H, 1, k0, 0, 0>(sm, sp, sinf, rb, re, own, stride, hs, trig_i); break;
+#define MCB200_COV_U2(k0, k1) \
+  case cov_pat(2, k0, k1): cov_layer_uniform<H, 2, k0, k1, 0>(sm, sp, sinf, rb, re, own, stride, hs, trig_i); break;
+#define MCB200_COV_U3(k0, k1, k2) \
+  case cov_pat(3, k0, k1, k2): cov_layer_uniform<H, 3, k0, k1, k2>(sm, sp, sinf, rb, re, own, stride, hs, trig_i); break;
+#define MCB200_COV_U2_ALL(k1) MCB200_COV_U2(0, k1) MCB200_COV_U2(1, k1) MCB200_COV_U2(2, k1)
+#define MCB200_COV_U3_ALL(k1, k2) MCB200_COV_U3(0, k1, k2) MCB200_COV_U3(1, k1, k2) MCB200_COV_U3(2, k1, k2)
+#define MCB200_COV_U3_ALL2(k2) MCB200_COV_U3_ALL(0, k2) MCB200_COV_U3_ALL(1, k2) MCB200_COV_U3_ALL(2, k2)
+
+template <int MT>
+__global__ void __launch_bounds__(128, (MT <= 4 ? 5 : 1)) expval_cov_kernel(
+    CovCircuit wc, const double* __restrict__ params, long long B, int ib, int trig_cap, const int8_t* init_bits,
+    const int8_t* target_bits, double floor2, double* __restrict__ out) {
+  using T = Tiles<MT>;
+  constexpr int H = (T::M + 31) / 32;
+  constexpr int ROWS = 32 * H, LD = ROWS + 1;
+  constexpr int LBUF = (ROWS * LD + 1) & ~1;  // doubles, even: the trig table behind it stays 16-byte aligned
+  static_assert(T::kScratch <= LBUF, "Pfaffian scratch aliases the covariance buffer");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Smem sm{smem_raw};
+  const int n = wc.n_qubits, d = 2 * n, ng = wc.n_gates;
+  const int warps = blockDim.x >> 5, w = warp_id(), lane = lane_id(), gr = lane >> 2, tg = lane & 3;
+  // block tables: sp[ng] (int4: physical rows of a run) | sinf[ng] (int4: trig byte offsets x3, pattern) |
+  //               strig[ng] | slayer[ng + 1] | slpat[ng] | counts[4] | phys[64]
+  int4* sp = reinterpret_cast<int4*>(smem_raw);
+  int4* sinf = sp + ng;
+  int* strig = reinterpret_cast<int*>(sinf + ng);
+  int* slayer = strig + ng;
+  int* slpat = slayer + ng + 1;
+  int* counts = slpat + ng;
+  unsigned char* sphys = reinterpret_cast<unsigned char*>(counts + 4);
+  const unsigned table_bytes = (unsigned)(((size_t)ng * 44 + 4 + 16 + 64 + 15) & ~(size_t)15);
+  const unsigned per_warp = (unsigned)((LBUF + 4 * trig_cap) * sizeof(double));
+  const unsigned lm_off = table_bytes + w * per_warp;     // this warp's Lambda
+  const unsigned trig_off = lm_off + LBUF * 8;            // this warp's sincos table
+  double* Lm = reinterpret_cast<double*>(smem_raw + lm_off);
+  double* trig = reinterpret_cast<double*>(smem_raw + trig_off);
+
+  // ---- block prologue: gate list -> run / layer / trig tables (instance independent)
+  {
+    mcb200_gate_t* tgates = reinterpret_cast<mcb200_gate_t*>(smem_raw + table_bytes);  // staging, dead afterwards
+    const int words = ng * (int)(sizeof(mcb200_gate_t) / sizeof(int));
+    for (int i = threadIdx.x; i < words; i += blockDim.x)
+      reinterpret_cast<int*>(tgates)[i] = reinterpret_cast<const int*>(wc.gates)[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int a = 0; a < 64; ++a) sphys[a] = (unsigned char)a;
+      int n_runs = 0, n_layers = 0, n_trig = 0, i = 0, layer_pat = 0;
+      unsigned long long layer_mask = 0ull;
+      slayer[0] = 0;
+      while (i < ng) {
+        const mcb200_gate_t g = tgates[i];
+        const int r0 = 2 * g.wire0;
+        if (g.kind == MCB200_GATE_FSWAP) {
+          // Lambda <- F^T Lambda F relabels: forward block phys'[a] = phys[a + 2 mod s], transposed phys[a - 2 mod s]
+          const int s = 2 * (g.wire1 - g.wire0 + 1);
+          unsigned char* p = sphys + r0;
+          if (!(g.flags & MCB200_GATE_FLAG_TRANSPOSE)) {
+            const unsigned char t0 = p[0], t1 = p[1];
+            for (int a = 0; a + 2 < s; ++a) p[a] = p[a + 2];
+            p[s - 2] = t0;
+            p[s - 1] = t1;
+          } else {
+            const unsigned char t0 = p[s - 2], t1 = p[s - 1];
+            for (int a = s - 1; a >= 2; --a) p[a] = p[a - 2];
+            p[0] = t0;
+            p[1] = t1;
+          }
+          ++i;
+          continue;
+        }
+        int len = 0, pat, toff[3] = {0, 0, 0};
+        if (g.kind <= MCB200_GATE_RZRZ) {
+          pat = 0;
+          while (i < ng && len < 3 && tgates[i].kind <= MCB200_GATE_RZRZ && tgates[i].wire0 == g.wire0) {
+            const int off = tgates[i].off;
+            int slot = -1;
+            for (int s2 = n_trig - 1; s2 >= 0 && s2 >= n_trig - 4; --s2)
+              if (strig[s2] == off) slot = s2;
+            if (slot < 0) {
+              slot = n_trig;
+              strig[n_trig++] = off;
+            }
+            toff[len] = 32 * slot;
+            pat |= tgates[i].kind << (2 + 2 * len);
+            ++len;
+            ++i;
+          }
+          pat |= len;
+        } else {
+          toff[0] = g.off;
+          pat = kPatBlock + (g.kind == MCB200_GATE_BLOCK4_PARAM ? 2 : 0) + ((g.flags & MCB200_GATE_FLAG_TRANSPOSE) ? 1 : 0);
+          ++i;
+        }
+        const int p0 = sphys[r0], p1 = sphys[r0 + 1], p2 = sphys[r0 + 2], p3 = sphys[r0 + 3];
+        const unsigned long long m = (1ull << p0) | (1ull << p1) | (1ull << p2) | (1ull << p3);
+        if (layer_mask & m) {
+          slpat[n_layers] = layer_pat;
+          slayer[++n_layers] = n_runs;
+          layer_mask = 0ull;
+        }
+        if (layer_mask == 0ull) layer_pat = pat >= kPatBlock ? kPatMixedLayer : pat;
+        else if (layer_pat != pat) layer_pat = kPatMixedLayer;
+        layer_mask |= m;
+        sp[n_runs] = make_int4(p0, p1, p2, p3);
+        sinf[n_runs] = make_int4(toff[0], toff[1], toff[2], pat);
+        ++n_runs;
+      }
+      if (n_runs > 0) {
+        slpat[n_layers] = layer_pat;
+        slayer[++n_layers] = n_runs;
+      }
+      counts[0] = n_runs;
+      counts[1] = n_layers;
+      counts[2] = n_trig;
+    }
+    __syncthreads();
+  }
+  const int n_layers = counts[1], n_trig = counts[2];
+
+  // initial-state sign per wire: Lambda_0[2k][2k+1] = -(-1)^bit_k
+  const bool lane_wire = lane < n;
+  const double s_init = (lane_wire && init_bits != nullptr && init_bits[lane]) ? 1.0 : -1.0;
+  // Pfaffian gather offsets through the final permutation: c[idx(ti,tj)][e] = L[phys[8ti+gr]][phys[8tj+2tg+e]]
+  unsigned rowoff[MT], coloff[MT][2];
+#pragma unroll
+  for (int t = 0; t < MT; ++t) {
+    rowoff[t] = lm_off + (unsigned)sphys[8 * t + gr] * (LD * 8);
+    coloff[t][0] = (unsigned)sphys[8 * t + 2 * tg] * 8;
+    coloff[t][1] = (unsigned)sphys[8 * t + 2 * tg + 1] * 8;
+  }
+  // + Lambda_y on the 2x2 diagonal blocks (both triangles of the diagonal tiles live in the fragments)
+  double ly[MT];
+#pragma unroll
+  for (int t = 0; t < MT; ++t) {
+    const int row = 8 * t + gr;
+    ly[t] = 0.0;
+    if (tg == (gr >> 1) && row < d) ly[t] = (target_bits != nullptr && target_bits[row >> 1]) ? 1.0 : -1.0;
+  }
+
+  const long long n_groups = (B + ib - 1) / ib;
+  for (long long grp = (long long)blockIdx.x * warps + w; grp < n_groups; grp += (long long)gridDim.x * warps) {
+    const long long b0 = grp * ib;
+    const int nb = (int)((B - b0) < ib ? (B - b0) : ib);
+    // ---- sincos of the half sum / half difference for every (instance, parameter column) pair of the group
+    __syncwarp();
+    for (int f = lane; f < nb * n_trig; f += 32) {
+      const int i = f / n_trig, s = f - i * n_trig;
+      const int off = strig[s];
+      const double* prow = params + (b0 + i) * wc.n_param_cols;
+      double p0 = prow[off], p1 = prow[off + 1];
+      if (wc.scale != nullptr) {
+        p0 = wc.bias[off] + wc.scale[off] * p0;
+        p1 = wc.bias[off + 1] + wc.scale[off + 1] * p1;
+      }
+      double ss, cs, sd, cd;
+      sincos(p0 / 2 + p1 / 2, &ss, &cs);
+      sincos(p0 / 2 - p1 / 2, &sd, &cd);
+      double2* t = reinterpret_cast<double2*>(trig + 4 * f);
+      t[0] = make_double2(cs, ss);
+      t[1] = make_double2(cd, sd);
+    }
+    for (int i = 0; i < nb; ++i) {
+      const unsigned trig_i = trig_off + 32u * (unsigned)(i * n_trig);
+      const double* prow = params + (b0 + i) * wc.n_param_cols;
+      // ---- Lambda = Lambda_0
+      __syncwarp();
+      for (int e = lane; e < LBUF / 2; e += 32) reinterpret_cast<double2*>(Lm)[e] = make_double2(0.0, 0.0);
+      __syncwarp();
+      if (lane_wire) {
+        Lm[(2 * lane) * LD + 2 * lane + 1] = s_init;
+        Lm[(2 * lane + 1) * LD + 2 * lane] = -s_init;
+      }
+      if (H > 1 && lane + 32 < n) {
+        const int k = lane + 32;
+        const double s2 = (init_bits != nullptr && init_bits[k]) ? 1.0 : -1.0;
+        Lm[(2 * k) * LD + 2 * k + 1] = s2;
+        Lm[(2 * k + 1) * LD + 2 * k] = -s2;
+      }
+      __syncwarp();
+      // ---- gates, layer by layer: rows of every run, barrier, columns of every run, barrier
+      for (int l = 0; l < n_layers; ++l) {
+        const int rb = slayer[l], re = slayer[l + 1], lpat = slpat[l];
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+          const unsigned stride = ph ? 8u : (unsigned)(LD * 8);               // of the gate's index
+          const unsigned own = lm_off + lane * (ph ? (unsigned)(LD * 8) : 8u);  // this lane's column / row
+          const unsigned hs = 32u * (ph ? (unsigned)(LD * 8) : 8u);
+          switch (lpat) {
+            MCB200_COV_U1(0) MCB200_COV_U1(1) MCB200_COV_U1(2)
+            MCB200_COV_U2_ALL(0) MCB200_COV_U2_ALL(1) MCB200_COV_U2_ALL(2)
+            MCB200_COV_U3_ALL2(0) MCB200_COV_U3_ALL2(1) MCB200_COV_U3_ALL2(2)
+            default: cov_layer_mixed<H>(sm, sp, sinf, rb, re, own, stride, hs, trig_i, wc.consts, prow); break;
+          }
+          __syncwarp();
+        }
+      }
+      // ---- Lambda (logical order) + Lambda_y -> DMMA accumulator fragments of the upper tiles
+      double c[T::NT][2];
+#pragma unroll
+      for (int ti = 0; ti < MT; ++ti)
+#pragma unroll
+        for (int tj = ti; tj < MT; ++tj) {
+          c[T::idx(ti, tj)][0] = sm.ld(rowoff[ti] + coloff[tj][0]);
+          c[T::idx(ti, tj)][1] = sm.ld(rowoff[ti] + coloff[tj][1]);
+        }
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        if (gr & 1) c[T::idx(t, t)][0] -= ly[t];
+        else c[T::idx(t, t)][1] += ly[t];
+      }
+      __syncwarp();  // every lane has read Lambda: the buffer becomes the Pfaffian's scratch
+      const double pf = warp_pfaffian_tiles<MT, 0, true>(c, d, Lm);  // Lambda|_W + Lambda_y of a physical state: bounded
+      if (lane == 0) out[b0 + i] = abs_floor(ldexp(pf, -n), floor2);
+    }
+  }
+}
+
+// Launch shape: warps per SM limited by shared memory; instances per sincos group chosen so that the groups divide
+// evenly over the resident warps (the batch of C2 gives each warp only ~25 instances: quantisation matters).
+int expval_cov_launch(const mcb200_circuit_t* h, const double* params, long long B, const int8_t* init_bits,
+                      const int8_t* target_bits, double* out, cudaStream_t st) {
+  CovCircuit wc{h->gates, h->n_gates, h->n_qubits, h->n_param_cols, h->scale, h->bias, h->consts};
+  const int d = 2 * h->n_qubits, ng = h->n_gates;
+  const int mt = d <= 8 ? 1 : d <= 16 ? 2 : d <= 24 ? 3 : d <= 32 ? 4 : d <= 48 ? 6 : 8;
+  const int Hh = mt <= 4 ? 1 : 2, rows = 32 * Hh, ld = rows + 1, lbuf = (rows * ld + 1) & ~1;
+  const int warps = 4;
+  const int n_trig_max = ng > 0 ? ng : 1;  // the kernel de-duplicates; the host only knows the upper bound
+  const int trig_cap = n_trig_max > 32 ? n_trig_max : 32;
+  const size_t table_bytes = ((size_t)ng * 44 + 4 + 16 + 64 + 15) & ~(size_t)15;
+  const size_t per_warp = ((size_t)lbuf + 4 * (size_t)trig_cap) * sizeof(double);
+  const size_t smem = table_bytes + warps * per_warp;
+  if (smem > (size_t)kMaxDynSmem || (size_t)ng * sizeof(mcb200_gate_t) > warps * per_warp) return -1;
+  int blocks_per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));
+  const int max_blocks_per_sm = mt <= 4 ? 5 : 1;
+  if (blocks_per_sm > max_blocks_per_sm) blocks_per_sm = max_blocks_per_sm;
+  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  // instances per group: at most trig_cap / n_trig pairs fit the table; n_trig is unknown here (<= ng), so the
+  // kernel is told the cap and the group size is chosen for the worst case n_trig = ng, except for the common
+  // shared-parameter circuits (n_param_cols == 2: one pair per instance) where 32 pairs = 32 instances fit
+  const int n_trig_bound = h->n_param_cols <= 2 ? 1 : n_trig_max;
+  int ib_max = trig_cap / n_trig_bound;
+  if (ib_max > 32) ib_max = 32;
+  if (ib_max < 1) ib_max = 1;
+  long long best_cost = -1;
+  int best_ib = 1, best_bps = blocks_per_sm;
+  for (int bps = blocks_per_sm; bps >= (blocks_per_sm > 1 ? blocks_per_sm - 1 : 1); --bps) {
+    const long long total_warps = (long long)kNumSMs * bps * warps;
+    for (int ib = 1; ib <= ib_max; ib *= 2) {
+      const long long groups = (B + ib - 1) / ib;
+      const long long rounds = (groups + total_warps - 1) / total_warps;
+      // per group: ib instances (~1500 warp instructions each) + one sincos pass (~250) per 32 (instance, column) pairs;
+      // fewer resident warps issue proportionally faster
+      const long long per_group = (long long)ib * 1500 + 250LL * ((ib * n_trig_bound + 31) / 32);
+      const long long cost = rounds * per_group * bps;
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_ib = ib;
+        best_bps = bps;
+      }
+    }
+  }
+  if (const char* e = getenv("MCB200_COV_IB")) {  // tuning experiments only (scripts/c2_routes_bench.py)
+    const int v = atoi(e);
+    if (v >= 1 && v <= ib_max) best_ib = v;
+  }
+  if (const char* e = getenv("MCB200_COV_BPS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= blocks_per_sm) best_bps = v;
+  }
+  const long long groups = (B + best_ib - 1) / best_ib;
+  long long blocks = (groups + warps - 1) / warps;
+  const long long cap = (long long)kNumSMs * best_bps;
+  if (blocks > cap) blocks = cap;
+  auto go = [&](auto kernel) -> int {
+    if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(expval_cov)"))
+      return rc;
+    kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(wc, params, B, best_ib, trig_cap, init_bits, target_bits,
+                                                      g_abs_floor2, out);
+    return check_launch("expval_cov_kernel");
+  };
+  switch (mt) {
+    case 1: return go(expval_cov_kernel<1>);
+    case 2: return go(expval_cov_kernel<2>);
+    case 3: return go(expval_cov_kernel<3>);
+    case 4: return go(expval_cov_kernel<4>);
+    case 6: return go(expval_cov_kernel<6>);
+    default: return go(expval_cov_kernel<8>);
+  }
+}
+
+}  // namespace mcb200

@@ -256,6 +256,14 @@ int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long lon
                        const int8_t* target_bits, double* out, cudaStream_t st) {
   WarpCircuit wc{h->gates, h->n_gates, h->n_qubits, h->n_param_cols, h->scale, h->bias, h->consts};
   const int d = 2 * h->n_qubits;
+  // Route: evolving the covariance gate by gate (expval_cov.cu, 24 d flop per rotation) beats building X = R and
+  // conjugating (12 d per rotation + d^3) while the circuit is shallow: n_gates (an upper bound of the number of
+  // rotations; the gate list lives in device memory) below d^2 / 12.
+  const int route = g_expval_route;
+  if (route == 2 || (route == 0 && 12LL * h->n_gates <= (long long)d * d)) {
+    const int rc = expval_cov_launch(h, params, B, init_bits, target_bits, out, st);
+    if (rc >= 0) return rc;  // -1: tables do not fit shared memory -> column route
+  }
   const int mt = d <= 8 ? 1 : d <= 16 ? 2 : d <= 24 ? 3 : d <= 32 ? 4 : d <= 48 ? 6 : 8;
   const int M = 8 * mt, LDX = M + 4;
   const int warps = 6;

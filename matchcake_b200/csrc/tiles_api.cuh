@@ -39,6 +39,10 @@ int cov_basis_gemm(const double* X, const int8_t* bits, long long B, int n_qubit
 struct CircuitDev;
 int circuit_columns_brick_launch(const CircuitDev& c, const double* params, long long B, const int32_t* cols, int m,
                                  double* X_out, cudaStream_t st);
+// covariance route of the fused projector kernel (expval_cov.cu); -1 = tables do not fit shared memory
+int expval_cov_launch(const mcb200_circuit_t* h, const double* params, long long B, const int8_t* init_bits,
+                      const int8_t* target_bits, double* out, cudaStream_t st);
+extern thread_local int g_expval_route;  // 0 = automatic, 1 = column route, 2 = covariance route (mcb200_set_expval_route)
 int expval_warp_launch(const mcb200_circuit_t* h, const double* params, long long B, const int8_t* init_bits,
                        const int8_t* target_bits, double* out, cudaStream_t st);
 }  // namespace mcb200

@@ -287,6 +287,76 @@ def test_fused_expval_projector_golden_and_batch():
         np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("route", [1, 2])
+@pytest.mark.parametrize("n", [2, 5, 8, 13, 16, 20, 32])
+def test_fused_expval_projector_routes_random_circuits(n, route):
+    """Both algorithms behind mcb200_circuit_expval_projector (1: X = R columns + DMMA conjugation, 2: covariance
+    evolved gate by gate) on random circuits: every rotation kind in runs of 1-4 on one wire pair, long-range fSWAPs in
+    both orientations, shared and per-instance explicit 4x4 blocks, excited initial and target bits, ragged batch."""
+    from matchcake_b200 import _lib
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(100 * n + route)
+    B = 37
+    names = ["SptmCompRxRx", "SptmCompRyRy", "SptmCompRzRz"]
+    ops = []
+    for _ in range(3 * n + 4):
+        k = int(rng.integers(0, 6)) if n > 2 else int(rng.integers(0, 3))
+        if k < 3:
+            w = int(rng.integers(0, n - 1))
+            for _ in range(int(rng.integers(1, 5))):
+                ops.append(Op(names[int(rng.integers(0, 3))], (w, w + 1), params=rng.uniform(0, 2 * np.pi, (B, 2))))
+        elif k < 5:
+            w0 = int(rng.integers(0, n - 1))
+            w1 = int(rng.integers(w0 + 1, n))
+            ops.append(Op("SptmFSwap", (w0, w1) if rng.random() < 0.5 else (w1, w0)))
+        else:
+            w = int(rng.integers(0, n - 1))
+            batched = rng.random() < 0.5
+            blk = gates.random_sptm(2, seed=int(rng.integers(1 << 30)), batch_size=B if batched else None)
+            ops.append(Op("Sptm", (w, w + 1), matrix=blk))
+    bits, tgt = rng.integers(0, 2, n), rng.integers(0, 2, n)
+    tgt[rng.integers(0, n)] ^= (bits.sum() + tgt.sum()) % 2  # same parity: non-trivial probability
+    r = gates.chain(ops, n, contraction=None)
+    ref = readout.probs_lookup_table(r, bits, tgt, np.arange(n))
+    circ, params = compiled(ops, n, B)
+    try:
+        _lib.set_expval_route(route)
+        out = mops.circuit_expval_projector(circ, params, torch.as_tensor(bits), torch.as_tensor(tgt)).cpu().numpy()
+    finally:
+        _lib.set_expval_route(0)
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("route", [1, 2])
+def test_fused_expval_projector_routes_shared_parameters(route):
+    """Config C2's structure (every gate reads parameter columns 0, 1; affine map on the angles) on both routes, batch
+    sizes around the group size of the covariance route's sincos pass."""
+    from matchcake_b200 import _lib
+    from matchcake_b200 import ops as mops
+
+    n = 16
+    rng = np.random.default_rng(5 + route)
+    specs = []
+    for w in range(0, n - 1, 2):
+        for kind in (mops.GATE_RXRX, mops.GATE_RYRY, mops.GATE_RZRZ):
+            specs.append(mops.GateSpec(kind, w, w + 1, 0))
+    for w in range(1, n - 1, 2):
+        specs.append(mops.GateSpec(mops.GATE_FSWAP, w, w + 1))
+    scale, bias = np.array([np.pi, 0.5]), np.array([0.3, -0.2])
+    for B in (1, 7, 8, 9, 33, 1000):
+        p = rng.uniform(0, 2, (B, 2))
+        circ = mops.CompiledCircuit(n, specs, 2, scale=scale, bias=bias)
+        try:
+            _lib.set_expval_route(route)
+            out = mops.circuit_expval_projector(circ, dev(p)).cpu().numpy()
+        finally:
+            _lib.set_expval_route(0)
+        zeros = np.zeros(n, int)
+        ref = readout.probs_lookup_table(gates.chain(readme_ops(n, bias + scale * p), n), zeros, zeros, np.arange(n))
+        np.testing.assert_allclose(out, ref, rtol=RTOL, atol=ATOL)
+
+
 def test_dense_path_tutorial_golden():
     """Random dense SPTM, product-state inputs: probabilities and Pauli-sum expectation values of the tutorials."""
     from matchcake_b200 import ops as mops
