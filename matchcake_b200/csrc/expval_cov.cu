@@ -13,6 +13,11 @@
 //  * Lambda (32H x 32H, stride 32H + 1: row AND column accesses are bank-conflict free) belongs to the warp.  A layer is
 //    applied as phase 0 (lane = column: rows p0..p3 <- G^T rows) for all its runs, then phase 1 (lane = row: columns
 //    p0..p3 <- columns G).  Left and right factors of disjoint gates commute, so a layer needs two warp barriers.
+//  * Light cone: the block prologue also propagates the STRUCTURAL non-zero pattern of Lambda through the gate list
+//    (bit rows, one warp).  While a layer's runs touch few non-zero columns the layer is executed from a packed list of
+//    (run, column) work items, 32 items per pass with per-lane addresses, instead of one 32-column pass per run:
+//    config C2's first layer (8 runs on a block-diagonal Lambda) is 2 passes instead of 16.  Dense layers keep the
+//    per-run passes.  Skipped elements are exact zeros, so the result does not change.
 //  * sincos is evaluated for a GROUP of instances at a time with (instance, parameter column) pairs spread over
 //    the lanes: config C2 has one parameter pair per instance, so a group of 8 instances costs one pass.
 //  * The Pfaffian reads Lambda through the final permutation straight into DMMA accumulator fragments; its scratch
@@ -120,6 +125,41 @@ __device__ __forceinline__ void cov_layer_uniform(const Smem sm, const int4* sp,
   }
 }
 
+// Packed (run, column) work items of one phase of a pattern-uniform layer: item = {a0 | a1 << 16, a2 | a3 << 16,
+// t0 | t1 << 16, t2}: byte offsets of the four elements within Lambda and of the sincos entries within the instance's table.
+template <int L, int K0, int K1, int K2>
+__device__ __forceinline__ void cov_items_uniform(const Smem sm, const uint4* items, int begin, int count, int lane,
+                                                  unsigned lm_off, unsigned trig_i) {
+#pragma unroll 1
+  for (int base = 0; base < count; base += 32) {
+    const bool act = base + lane < count;
+    const uint4 it = items[begin + (act ? base + lane : 0)];
+    const unsigned a0 = lm_off + (it.x & 0xffffu), a1 = lm_off + (it.x >> 16), a2 = lm_off + (it.y & 0xffffu),
+                   a3 = lm_off + (it.y >> 16);
+    double2 ca[L], cb[L];
+    ca[0] = sm.ld2(trig_i + (it.z & 0xffffu));
+    cb[0] = sm.ld2(trig_i + (it.z & 0xffffu) + 16);
+    if constexpr (L > 1) {
+      ca[1] = sm.ld2(trig_i + (it.z >> 16));
+      cb[1] = sm.ld2(trig_i + (it.z >> 16) + 16);
+    }
+    if constexpr (L > 2) {
+      ca[2] = sm.ld2(trig_i + it.w);
+      cb[2] = sm.ld2(trig_i + it.w + 16);
+    }
+    double x[4] = {sm.ld(a0), sm.ld(a1), sm.ld(a2), sm.ld(a3)};
+    cov_rotation<K0>(x, ca[0], cb[0]);
+    if constexpr (L > 1) cov_rotation<K1>(x, ca[1], cb[1]);
+    if constexpr (L > 2) cov_rotation<K2>(x, ca[2], cb[2]);
+    if (act) {
+      sm.st(a0, x[0]);
+      sm.st(a1, x[1]);
+      sm.st(a2, x[2]);
+      sm.st(a3, x[3]);
+    }
+  }
+}
+
 // Layer with mixed patterns (or explicit 4x4 blocks): per-run decode, per-gate branch on the kind.
 template <int H>
 __device__ __forceinline__ void cov_layer_mixed(const Smem sm, const int4* sp, const int4* sinf, int rb, int re,
@@ -169,20 +209,24 @@ __device__ __forceinline__ void cov_layer_mixed(const Smem sm, const int4* sp, c
   }
 }
 
-#define MCB200_COV_U1(k0) \
-  case cov_pat(1, k0): cov_layer_uniform<H, 1, k0, 0, 0>(sm, sp, sinf, rb, re, own, stride, hs, trig_i); break;
-#define MCB200_COV_U2(k0, k1) \
-  case cov_pat(2, k0, k1): cov_layer_uniform<H, 2, k0, k1, 0>(sm, sp, sinf, rb, re, own, stride, hs, trig_i); break;
-#define MCB200_COV_U3(k0, k1, k2) \
-  case cov_pat(3, k0, k1, k2): cov_layer_uniform<H, 3, k0, k1, k2>(sm, sp, sinf, rb, re, own, stride, hs, trig_i); break;
+#define MCB200_COV_CASE(L, k0, k1, k2)                                                                      \
+  case cov_pat(L, k0, k1, k2):                                                                               \
+    if (icnt >= 0) cov_items_uniform<L, k0, k1, k2>(sm, sitems, ibeg, icnt, lane, lm_off, trig_i);           \
+    else cov_layer_uniform<H, L, k0, k1, k2>(sm, sp, sinf, rb, re, own, stride, hs, trig_i);                  \
+    break;
+#define MCB200_COV_U1(k0) MCB200_COV_CASE(1, k0, 0, 0)
+#define MCB200_COV_U2(k0, k1) MCB200_COV_CASE(2, k0, k1, 0)
+#define MCB200_COV_U3(k0, k1, k2) MCB200_COV_CASE(3, k0, k1, k2)
 #define MCB200_COV_U2_ALL(k1) MCB200_COV_U2(0, k1) MCB200_COV_U2(1, k1) MCB200_COV_U2(2, k1)
 #define MCB200_COV_U3_ALL(k1, k2) MCB200_COV_U3(0, k1, k2) MCB200_COV_U3(1, k1, k2) MCB200_COV_U3(2, k1, k2)
 #define MCB200_COV_U3_ALL2(k2) MCB200_COV_U3_ALL(0, k2) MCB200_COV_U3_ALL(1, k2) MCB200_COV_U3_ALL(2, k2)
 
+constexpr int cov_warps(int mt) { return mt <= 4 ? 10 : 6; }  // per block; 2 blocks (1 for 2N > 32) per SM
+
 template <int MT>
-__global__ void __launch_bounds__(128, (MT <= 4 ? 5 : 1)) expval_cov_kernel(
-    CovCircuit wc, const double* __restrict__ params, long long B, int ib, int trig_cap, const int8_t* init_bits,
-    const int8_t* target_bits, double floor2, double* __restrict__ out) {
+__global__ void __launch_bounds__(32 * cov_warps(MT), (MT <= 4 ? 2 : 1)) expval_cov_kernel(
+    CovCircuit wc, const double* __restrict__ params, long long B, int ib, int trig_cap, int item_cap,
+    const int8_t* init_bits, const int8_t* target_bits, double floor2, double* __restrict__ out) {
   using T = Tiles<MT>;
   constexpr int H = (T::M + 31) / 32;
   constexpr int ROWS = 32 * H, LD = ROWS + 1;
@@ -193,15 +237,18 @@ __global__ void __launch_bounds__(128, (MT <= 4 ? 5 : 1)) expval_cov_kernel(
   const int n = wc.n_qubits, d = 2 * n, ng = wc.n_gates;
   const int warps = blockDim.x >> 5, w = warp_id(), lane = lane_id(), gr = lane >> 2, tg = lane & 3;
   // block tables: sp[ng] (int4: physical rows of a run) | sinf[ng] (int4: trig byte offsets x3, pattern) |
+  //               slitem[ng] (int4: item range of phase 0 / phase 1 of a layer, count -1 = dense) | sitems[item_cap] |
   //               strig[ng] | slayer[ng + 1] | slpat[ng] | counts[4] | phys[64]
   int4* sp = reinterpret_cast<int4*>(smem_raw);
   int4* sinf = sp + ng;
-  int* strig = reinterpret_cast<int*>(sinf + ng);
+  int4* slitem = sinf + ng;
+  uint4* sitems = reinterpret_cast<uint4*>(slitem + ng);
+  int* strig = reinterpret_cast<int*>(sitems + item_cap);
   int* slayer = strig + ng;
   int* slpat = slayer + ng + 1;
   int* counts = slpat + ng;
   unsigned char* sphys = reinterpret_cast<unsigned char*>(counts + 4);
-  const unsigned table_bytes = (unsigned)(((size_t)ng * 44 + 4 + 16 + 64 + 15) & ~(size_t)15);
+  const unsigned table_bytes = (unsigned)(((size_t)ng * 60 + (size_t)item_cap * 16 + 4 + 16 + 64 + 15) & ~(size_t)15);
   const unsigned per_warp = (unsigned)((LBUF + 4 * trig_cap) * sizeof(double));
   const unsigned lm_off = table_bytes + w * per_warp;     // this warp's Lambda
   const unsigned trig_off = lm_off + LBUF * 8;            // this warp's sincos table
@@ -287,6 +334,92 @@ __global__ void __launch_bounds__(128, (MT <= 4 ? 5 : 1)) expval_cov_kernel(
       counts[2] = n_trig;
     }
     __syncthreads();
+    // ---- structural pattern of Lambda, layer by layer (warp 0; lane q holds the bit rows q and q + 32) -> work items
+    if (w == 0) {
+      const int n_layers0 = counts[1];
+      unsigned long long* tmask = reinterpret_cast<unsigned long long*>(tgates);  // per run of the layer: U, then V
+      unsigned long long S0 = lane < d ? 1ull << (lane ^ 1) : 0ull;               // Lambda_0: index q couples to q ^ 1
+      unsigned long long S1 = lane + 32 < d ? 1ull << ((lane + 32) ^ 1) : 0ull;
+      int n_items = 0;
+      const unsigned lt = (1u << lane) - 1u;
+      for (int l = 0; l < n_layers0; ++l) {
+        const int rb = slayer[l], re = slayer[l + 1], lpat = slpat[l];
+        int cnt0 = 0, cnt1 = 0;
+        // phase 0 of run r touches the columns U_r = union of the patterns of its four rows
+        for (int r = rb; r < re; ++r) {
+          const int4 p = sp[r];
+          unsigned long long U = 0ull;
+          const int pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const unsigned long long a = __shfl_sync(0xffffffffu, S0, pp[k] & 31), b = __shfl_sync(0xffffffffu, S1, pp[k] & 31);
+            U |= pp[k] < 32 ? a : b;
+          }
+          if (lane == 0) tmask[2 * (r - rb)] = U;
+          cnt0 += __popcll(U);
+        }
+        __syncwarp();
+        for (int r = rb; r < re; ++r) {  // ... and leaves that pattern in all four rows
+          const int4 p = sp[r];
+          const unsigned long long U = tmask[2 * (r - rb)];
+          const int pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (lane == (pp[k] & 31)) {
+              if (pp[k] < 32) S0 = U;
+              else S1 = U;
+            }
+          }
+        }
+        // phase 1 of run r touches the rows V_r whose pattern meets the run's four columns, and fills those columns
+        for (int r = rb; r < re; ++r) {
+          const int4 p = sp[r];
+          const unsigned long long mP = (1ull << p.x) | (1ull << p.y) | (1ull << p.z) | (1ull << p.w);
+          const bool h0 = (S0 & mP) != 0ull, h1 = (S1 & mP) != 0ull;
+          const unsigned long long V = (unsigned long long)__ballot_sync(0xffffffffu, h0) |
+                                       ((unsigned long long)__ballot_sync(0xffffffffu, h1) << 32);
+          if (h0) S0 |= mP;
+          if (h1) S1 |= mP;
+          if (lane == 0) tmask[2 * (r - rb) + 1] = V;
+          cnt1 += __popcll(V);
+        }
+        __syncwarp();
+        const int passes_sparse = (cnt0 + 31) / 32 + (cnt1 + 31) / 32, passes_dense = 2 * (re - rb) * H;
+        const bool sparse = lpat != kPatMixedLayer && passes_sparse < passes_dense && n_items + cnt0 + cnt1 <= item_cap &&
+                            counts[2] <= 2047;
+        if (sparse) {
+          int pos = n_items;
+          for (int ph = 0; ph < 2; ++ph) {
+            for (int r = rb; r < re; ++r) {
+              const int4 p = sp[r];
+              const int4 ti = sinf[r];
+              const unsigned long long mask = tmask[2 * (r - rb) + ph];
+              const unsigned lo = (unsigned)mask, hi = (unsigned)(mask >> 32);
+              const int pp[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const unsigned word = half ? hi : lo;
+                if ((word >> lane) & 1u) {
+                  const int q = lane + 32 * half;  // column (phase 0) / row (phase 1)
+                  unsigned a[4];
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) a[k] = ph == 0 ? (unsigned)(pp[k] * LD + q) * 8u : (unsigned)(q * LD + pp[k]) * 8u;
+                  sitems[pos + (half ? __popc(lo) : 0) + __popc(word & lt)] =
+                      make_uint4(a[0] | (a[1] << 16), a[2] | (a[3] << 16), (unsigned)ti.x | ((unsigned)ti.y << 16), (unsigned)ti.z);
+                }
+              }
+              pos += __popcll(mask);
+            }
+          }
+          if (lane == 0) slitem[l] = make_int4(n_items, cnt0, n_items + cnt0, cnt1);
+          n_items += cnt0 + cnt1;
+        } else if (lane == 0) {
+          slitem[l] = make_int4(0, -1, 0, -1);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
   }
   const int n_layers = counts[1], n_trig = counts[2];
 
@@ -310,6 +443,7 @@ __global__ void __launch_bounds__(128, (MT <= 4 ? 5 : 1)) expval_cov_kernel(
     if (tg == (gr >> 1) && row < d) ly[t] = (target_bits != nullptr && target_bits[row >> 1]) ? 1.0 : -1.0;
   }
 
+  const double scale = __hiloint2double((1023 - n) << 20, 0);  // 2^-n, exact
   const long long n_groups = (B + ib - 1) / ib;
   for (long long grp = (long long)blockIdx.x * warps + w; grp < n_groups; grp += (long long)gridDim.x * warps) {
     const long long b0 = grp * ib;
@@ -353,11 +487,13 @@ __global__ void __launch_bounds__(128, (MT <= 4 ? 5 : 1)) expval_cov_kernel(
       // ---- gates, layer by layer: rows of every run, barrier, columns of every run, barrier
       for (int l = 0; l < n_layers; ++l) {
         const int rb = slayer[l], re = slayer[l + 1], lpat = slpat[l];
+        const int4 li = slitem[l];
 #pragma unroll 1
         for (int ph = 0; ph < 2; ++ph) {
           const unsigned stride = ph ? 8u : (unsigned)(LD * 8);               // of the gate's index
           const unsigned own = lm_off + lane * (ph ? (unsigned)(LD * 8) : 8u);  // this lane's column / row
           const unsigned hs = 32u * (ph ? (unsigned)(LD * 8) : 8u);
+          const int ibeg = ph ? li.z : li.x, icnt = ph ? li.w : li.y;          // packed work items (count < 0: dense)
           switch (lpat) {
             MCB200_COV_U1(0) MCB200_COV_U1(1) MCB200_COV_U1(2)
             MCB200_COV_U2_ALL(0) MCB200_COV_U2_ALL(1) MCB200_COV_U2_ALL(2)
@@ -383,72 +519,63 @@ __global__ void __launch_bounds__(128, (MT <= 4 ? 5 : 1)) expval_cov_kernel(
       }
       __syncwarp();  // every lane has read Lambda: the buffer becomes the Pfaffian's scratch
       const double pf = warp_pfaffian_tiles<MT, 0, true>(c, d, Lm);  // Lambda|_W + Lambda_y of a physical state: bounded
-      if (lane == 0) out[b0 + i] = abs_floor(ldexp(pf, -n), floor2);
+      if (lane == 0) out[b0 + i] = abs_floor(pf * scale, floor2);
     }
   }
 }
 
-// Launch shape: warps per SM limited by shared memory; instances per sincos group chosen so that the groups divide
-// evenly over the resident warps (the batch of C2 gives each warp only ~25 instances: quantisation matters).
+// Launch shape: two blocks of 10 warps per SM (one of 6 beyond 32 Majorana modes), limited by shared memory; instances
+// per sincos group chosen so that the groups divide evenly over the resident warps (the batch of C2 gives each warp
+// only ~22 instances: quantisation matters).
 int expval_cov_launch(const mcb200_circuit_t* h, const double* params, long long B, const int8_t* init_bits,
                       const int8_t* target_bits, double* out, cudaStream_t st) {
   CovCircuit wc{h->gates, h->n_gates, h->n_qubits, h->n_param_cols, h->scale, h->bias, h->consts};
   const int d = 2 * h->n_qubits, ng = h->n_gates;
   const int mt = d <= 8 ? 1 : d <= 16 ? 2 : d <= 24 ? 3 : d <= 32 ? 4 : d <= 48 ? 6 : 8;
   const int Hh = mt <= 4 ? 1 : 2, rows = 32 * Hh, ld = rows + 1, lbuf = (rows * ld + 1) & ~1;
-  const int warps = 4;
+  const int warps = cov_warps(mt), bps = mt <= 4 ? 2 : 1;
   const int n_trig_max = ng > 0 ? ng : 1;  // the kernel de-duplicates; the host only knows the upper bound
   const int trig_cap = n_trig_max > 32 ? n_trig_max : 32;
-  const size_t table_bytes = ((size_t)ng * 44 + 4 + 16 + 64 + 15) & ~(size_t)15;
+  int item_cap = 16 * ng;                  // packed work items (16 B each) of the sparse layers
+  if (item_cap > 512) item_cap = 512;
+  if (const char* e = getenv("MCB200_COV_ITEMS")) item_cap = atoi(e) > 0 ? atoi(e) : 0;  // tuning experiments only
+  const size_t table_bytes = ((size_t)ng * 60 + (size_t)item_cap * 16 + 4 + 16 + 64 + 15) & ~(size_t)15;
   const size_t per_warp = ((size_t)lbuf + 4 * (size_t)trig_cap) * sizeof(double);
   const size_t smem = table_bytes + warps * per_warp;
-  if (smem > (size_t)kMaxDynSmem || (size_t)ng * sizeof(mcb200_gate_t) > warps * per_warp) return -1;
-  int blocks_per_sm = (int)((size_t)(228 * 1024) / (smem + 1024));
-  const int max_blocks_per_sm = mt <= 4 ? 5 : 1;
-  if (blocks_per_sm > max_blocks_per_sm) blocks_per_sm = max_blocks_per_sm;
-  if (blocks_per_sm < 1) blocks_per_sm = 1;
+  if (smem > (size_t)(228 * 1024) / bps - 1024 || (size_t)ng * (sizeof(mcb200_gate_t) + 16) > warps * per_warp) return -1;
   // instances per group: at most trig_cap / n_trig pairs fit the table; n_trig is unknown here (<= ng), so the
-  // kernel is told the cap and the group size is chosen for the worst case n_trig = ng, except for the common
-  // shared-parameter circuits (n_param_cols == 2: one pair per instance) where 32 pairs = 32 instances fit
+  // group size is chosen for the worst case n_trig = ng, except for the common shared-parameter circuits
+  // (n_param_cols == 2: one pair per instance) where 32 pairs = 32 instances fit
   const int n_trig_bound = h->n_param_cols <= 2 ? 1 : n_trig_max;
   int ib_max = trig_cap / n_trig_bound;
   if (ib_max > 32) ib_max = 32;
   if (ib_max < 1) ib_max = 1;
   long long best_cost = -1;
-  int best_ib = 1, best_bps = blocks_per_sm;
-  for (int bps = blocks_per_sm; bps >= (blocks_per_sm > 1 ? blocks_per_sm - 1 : 1); --bps) {
-    const long long total_warps = (long long)kNumSMs * bps * warps;
-    for (int ib = 1; ib <= ib_max; ib *= 2) {
-      const long long groups = (B + ib - 1) / ib;
-      const long long rounds = (groups + total_warps - 1) / total_warps;
-      // per group: ib instances (~1500 warp instructions each) + one sincos pass (~250) per 32 (instance, column) pairs;
-      // fewer resident warps issue proportionally faster
-      const long long per_group = (long long)ib * 1500 + 250LL * ((ib * n_trig_bound + 31) / 32);
-      const long long cost = rounds * per_group * bps;
-      if (best_cost < 0 || cost < best_cost) {
-        best_cost = cost;
-        best_ib = ib;
-        best_bps = bps;
-      }
+  int best_ib = 1;
+  const long long total_warps = (long long)kNumSMs * bps * warps;
+  for (int ib = 1; ib <= ib_max; ib *= 2) {
+    const long long groups = (B + ib - 1) / ib;
+    const long long rounds = (groups + total_warps - 1) / total_warps;
+    // per group: ib instances (~1300 warp instructions each) + one sincos pass (~250) per 32 (instance, column) pairs
+    const long long cost = rounds * ((long long)ib * 1300 + 250LL * ((ib * n_trig_bound + 31) / 32));
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_ib = ib;
     }
   }
   if (const char* e = getenv("MCB200_COV_IB")) {  // tuning experiments only (scripts/c2_routes_bench.py)
     const int v = atoi(e);
     if (v >= 1 && v <= ib_max) best_ib = v;
   }
-  if (const char* e = getenv("MCB200_COV_BPS")) {
-    const int v = atoi(e);
-    if (v >= 1 && v <= blocks_per_sm) best_bps = v;
-  }
   const long long groups = (B + best_ib - 1) / best_ib;
   long long blocks = (groups + warps - 1) / warps;
-  const long long cap = (long long)kNumSMs * best_bps;
+  const long long cap = (long long)kNumSMs * bps;
   if (blocks > cap) blocks = cap;
   auto go = [&](auto kernel) -> int {
     if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(expval_cov)"))
       return rc;
-    kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(wc, params, B, best_ib, trig_cap, init_bits, target_bits,
+    kernel<<<(unsigned)blocks, warps * 32, smem, st>>>(wc, params, B, best_ib, trig_cap, item_cap, init_bits, target_bits,
                                                       g_abs_floor2, out);
     return check_launch("expval_cov_kernel");
   };

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(32 * TI * TJ, MINB) gram_tiles_kernel(GramTile
         c[q][1] = x.y + y.y;
       }
     }
-    const double pf = warp_pfaffian_tiles<MT, SR>(c, g.m, scratch, sm);
+    const double pf = warp_pfaffian_tiles<MT, SR, false, true>(c, g.m, scratch, sm);  // Lambda_i + Lambda_j
     if (lane == 0) {
       const double v = abs_floor(g.scale * pf, g.floor2);
       g.K[i * g.ldk + j] = v;

@@ -242,15 +242,30 @@ __device__ double warp_pfaffian_tiles_pivoted(double (&c)[Tiles<MT>::NT][2], int
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Static-order fast path.  Pair S = (2S, 2S+1) is eliminated with pivot A[2S][2S+1] -- no search, no permutation,
-// every tile / lane index is a compile-time constant, so a step is: predicated row stores, a reciprocal, 2 loads + 2
-// multiplies per live tile index and one DMMA per live tile (several times fewer instructions than the pivoted
-// step), and two pairs share one pass over the tiles (rank-4 update, see warp_pfaffian_static_steps).  For the matrices of this path (Lambda|_W + Lambda_y, Lambda_i + Lambda_j) the natural pivot is the
-// conditional probability of the target outcome and is rarely small.  A guard keeps the accuracy of partial pivoting:
-// the step is taken only if |pivot| >= kStaticPivotRatio * max_j |A[2S][j]| (multipliers <= 1/ratio); otherwise the
-// routine stops and reports how many indices it eliminated, and the pivoted routine finishes the remaining Schur
-// complement (warp_pfaffian_tiles_pivoted(..., start)).
-constexpr double kStaticPivotRatio = 1e-3;
+// Static-order fast path: 4 x 4 BLOCK pivots.  Quadruple D eliminates the indices R .. R+3 (R = 4D) with the leading
+// 4 x 4 block B = A[R:R+4, R:R+4] as the pivot -- no search, no permutation, every tile / lane index a compile-time
+// constant.  With  a = B01, b = B02, c = B03, d = B12, e = B13, f = B23:
+//      q = Pf(B) = a f - b e + c d,        B^-1 = 1/q [[0,-f,e,-d],[f,0,-c,b],[-e,c,0,-a],[d,-b,a,0]],
+//      Pf(A) = q Pf(A'),                   A' = A_22 + r^T (B^-1 r)      (r = the four rows R .. R+3, trailing columns),
+// so the whole rank-4 update is ONE K = 4 DMMA per live upper tile with A-fragment columns r_k and B-fragment rows
+// y_k = (B^-1 r)_k.  Lane tg = k builds its own row y_k on the fly while it loads the B fragment: three scalars
+// (block entries times 1/q) times three of the four row vectors -- one reciprocal, one warp barrier and no second pass
+// over the vectors per quadruple (the sequential variant it replaces spent two reciprocals, two barriers, a rank-2
+// update of rows R+2, R+3 in shared memory and a multiply per fragment entry).  For the matrices of this path
+// (Lambda|_W + Lambda_y, Lambda_i + Lambda_j) q is a product of two conditional probabilities of the target outcome
+// and is rarely small.  A guard keeps the accuracy of partial pivoting: the quadruple is taken only if the entries
+// of the update r^T B^-1 r cannot exceed kStaticBlockGrowth times the current scale,  s sB / |q| <= growth  with
+// s = largest |entry| of the four rows (2 when BOUNDED) and sB = sum of the |entries| of B (random Gaussian matrices:
+// same accuracy as scalar pivots guarded at 1e-3 of their row, measured); otherwise the routine stops, reports how many indices it eliminated, and the pivoted routine finishes the remaining
+// Schur complement (warp_pfaffian_tiles_pivoted(..., start)).  A block pivot is also the more robust choice: it does
+// not care whether A[R][R+1] alone is small.
+constexpr double kStaticBlockGrowth = 1e3;           // arbitrary matrices (utils.pfaffian, sector features)
+// Lambda|_W + Lambda_y and Lambda_i + Lambda_j: the Schur complements of these sums of covariances stay O(1), the bound
+// s sB / |q| only measures the rounding amplification of the update (<= 1e5 eps); on config C3's cells it reaches 6e4
+// at the 99.9 % quantile with a worst error of 1e-14 (measured), and 1e3 would hand 12 % of the cells to the pivoted
+// routine for nothing.
+constexpr double kStaticBlockGrowthPhysical = 1e5;
+constexpr double kStaticPivotRatio = 1e-3;  // scalar-pivot guard of the block-per-matrix variant (pfaffian_block_tiles.cu)
 
 // 1 / x for a normal, non-zero x (the guard has just checked it): hardware seed (~20 bits) + two Newton steps instead
 // of the IEEE division sequence with its special-case handling; full double accuracy, half the instructions.
@@ -271,126 +286,143 @@ __device__ __forceinline__ void static_store_rows(const double (&c)[Tiles<MT>::N
   }
 }
 
-// Guard of one static pivot: |piv| against the largest |row[j]|, j > last (or against the bound 2 when BOUNDED: the
-// caller guarantees |A[i][j]| <= 2 for the matrix and all its Schur complements -- Lambda|_W + Lambda_y of a physical
-// state, whose conditional covariance after each projected wire is again a covariance).
-template <int M, bool BOUNDED>
-__device__ __forceinline__ bool static_pivot_ok(double piv, const double* row, int last) {
-  if constexpr (BOUNDED) {
-    return fabs(piv) >= 2.0 * kStaticPivotRatio;
+// Per-lane constants of the static path (the same for every quadruple): row R + k lives in vector slot brev2(k), so
+// that consecutive rows are 8 doubles apart modulo the 128-byte bank line (vector stride M + 4): the 16-byte row stores
+// of a quarter warp and the 8-byte fragment loads of a half warp are conflict free.
+template <int MT>
+struct StaticLane {
+  const double* a_vec;     // A fragment: row R + tg at column gr
+  const double* y_vec[3];  // the three rows != tg at column gr (B fragment: y_tg = sum_j coef_j * row_j)
+  const double* y_ent[3];  // block entry behind coef_j: slot row + column offset (add R)
+  double y_sgn[3];         // its sign in B^-1
+  double* st;              // where this lane stores its part of row R + (gr & 3)
+};
+
+__host__ __device__ constexpr int static_slot(int k) { return ((k & 1) << 1) | (k >> 1); }
+
+template <int MT>
+__device__ __forceinline__ StaticLane<MT> static_lane_setup(double* scratch) {
+  constexpr int VS = Tiles<MT>::M + 4;
+  const int lane = lane_id(), gr = lane >> 2, tg = lane & 3;
+  StaticLane<MT> L;
+  L.a_vec = scratch + static_slot(tg) * VS + gr;
+  L.st = scratch + static_slot(gr & 3) * VS + 2 * tg;
+  // y_0 = (-f r1 + e r2 - d r3)/q, y_1 = (f r0 - c r2 + b r3)/q, y_2 = (-e r0 + c r1 - a r3)/q, y_3 = (d r0 - b r1 + a r2)/q
+  // entries: a = row0[R+1], b = row0[R+2], c = row0[R+3], d = row1[R+2], e = row1[R+3], f = row2[R+3]
+  int row[3], erow[3], ecol[3];
+  if (tg == 0) {
+    row[0] = 1; erow[0] = 2; ecol[0] = 3; L.y_sgn[0] = -1.0;  // f
+    row[1] = 2; erow[1] = 1; ecol[1] = 3; L.y_sgn[1] = 1.0;   // e
+    row[2] = 3; erow[2] = 1; ecol[2] = 2; L.y_sgn[2] = -1.0;  // d
+  } else if (tg == 1) {
+    row[0] = 0; erow[0] = 2; ecol[0] = 3; L.y_sgn[0] = 1.0;   // f
+    row[1] = 2; erow[1] = 0; ecol[1] = 3; L.y_sgn[1] = -1.0;  // c
+    row[2] = 3; erow[2] = 0; ecol[2] = 2; L.y_sgn[2] = 1.0;   // b
+  } else if (tg == 2) {
+    row[0] = 0; erow[0] = 1; ecol[0] = 3; L.y_sgn[0] = -1.0;  // e
+    row[1] = 1; erow[1] = 0; ecol[1] = 3; L.y_sgn[1] = 1.0;   // c
+    row[2] = 3; erow[2] = 0; ecol[2] = 1; L.y_sgn[2] = -1.0;  // a
   } else {
-    const int lane = lane_id();
-    unsigned key = 0u;
-    if (lane > last && lane < M) key = (unsigned)__double2hiint(row[lane]) & 0x7fffffffu;
-    if constexpr (M > 32) {
-      if (lane + 32 < M && lane + 32 > last) {
-        const unsigned k2 = (unsigned)__double2hiint(row[lane + 32]) & 0x7fffffffu;
+    row[0] = 0; erow[0] = 1; ecol[0] = 2; L.y_sgn[0] = 1.0;   // d
+    row[1] = 1; erow[1] = 0; ecol[1] = 2; L.y_sgn[1] = -1.0;  // b
+    row[2] = 2; erow[2] = 0; ecol[2] = 1; L.y_sgn[2] = 1.0;   // a
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    L.y_vec[j] = scratch + static_slot(row[j]) * VS + gr;
+    L.y_ent[j] = scratch + static_slot(erow[j]) * VS + ecol[j];
+  }
+  return L;
+}
+
+// Largest |entry| (as the high word of the double) of rows R .. R+3 over the columns > last.
+template <int M>
+__device__ __forceinline__ unsigned static_rows_max_key(const double* scratch, int last) {
+  constexpr int VS = M + 4;
+  const int lane = lane_id();
+  unsigned key = 0u;
+#pragma unroll
+  for (int q = 0; q < (M + 31) / 32; ++q) {
+    const int cc = lane + 32 * q;
+    if (cc > last && cc < M) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned k2 = (unsigned)__double2hiint(scratch[k * VS + cc]) & 0x7fffffffu;
         key = k2 > key ? k2 : key;
       }
     }
-    const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
-    return fabs(piv) >= kStaticPivotRatio * __hiloint2double((int)kmax, 0) && piv != 0.0;
   }
+  return __reduce_max_sync(0xffffffffu, key);
 }
 
-// Double step D eliminates the pairs (4D, 4D+1) and (4D+2, 4D+3) and applies BOTH rank-2 updates to the trailing tiles
-// as one K = 4 DMMA per tile:  A += w tau^T - tau w^T + w' tau'^T - tau' w'^T  with
-//   A-fragment columns (w, -tau, w', -tau'),  B-fragment rows (tau; w; tau'; w')
-// (tau = row 4D / piv1, w = row 4D+1; tau', w' the same for rows 4D+2, 4D+3 AFTER the first pair's update, which is
-// applied to those two rows only, as vectors in shared memory).  Half the tensor instructions of two rank-2 steps and
-// no wasted K lanes.  Returns the number of eliminated indices (m when the whole matrix went through); pf is
-// multiplied by the pivots taken.
-template <int MT, int SR, bool BOUNDED = false, int D = 0>
+// Returns the number of eliminated indices (m when the whole matrix went through); pf is multiplied by the pivots taken.
+template <int MT, int SR, bool BOUNDED = false, bool PHYSICAL = BOUNDED, int D = 0>
 __device__ __forceinline__ int warp_pfaffian_static_steps(double (&c)[Tiles<MT>::NT][2], int m, double* scratch,
-                                                          double2* sm, double& pf) {
+                                                          double2* sm, double& pf, const StaticLane<MT>& L) {
   using T = Tiles<MT>;
   if constexpr (4 * D >= T::M) {
     return m;
   } else {
     constexpr int R = 4 * D, TR = R >> 3;
-    constexpr int VS = T::M + 4;  // vector stride: the 4 vectors start 4 doubles apart modulo a 128-byte bank line
+    constexpr int VS = T::M + 4;
     if (R >= m) return m;
-    const int lane = lane_id(), gr = lane >> 2, tg = lane & 3;
-    // row R + k lives in slot brev2(k): consecutive rows are then 8 doubles apart modulo the bank line, so the 16-byte
-    // row stores of a quarter warp (two rows) as well as the 8-byte fragment loads of a half warp (four vectors, four
-    // consecutive entries each) are conflict free
-    double* u = scratch;             // row R
-    double* v = scratch + 2 * VS;    // row R + 1
-    double* u2 = scratch + VS;       // row R + 2
-    double* v2 = scratch + 3 * VS;   // row R + 3
+    const int lane = lane_id(), gr = lane >> 2;
+    const double* u = scratch;             // row R      (slot 0)
+    const double* v = scratch + 2 * VS;    // row R + 1  (slot 2)
+    const double* u2 = scratch + VS;       // row R + 2  (slot 1)
     // (1) rows R .. R+3 of tile row TR -> shared vectors (held by the lanes with gr >> 2 == D & 1)
-    if ((gr >> 2) == (D & 1))
-      static_store_rows<MT, SR, TR, TR>(c, sm, scratch + (((gr & 1) << 1) | ((gr >> 1) & 1)) * VS + 2 * tg);
+    if ((gr >> 2) == (D & 1)) static_store_rows<MT, SR, TR, TR>(c, sm, L.st);
     __syncwarp();
-    const double piv1 = u[R + 1];
-    if (!static_pivot_ok<T::M, BOUNDED>(piv1, u, R + 1)) return R;
-    pf *= piv1;
-    if (R + 2 >= m) return m;  // last pair: nothing left to update
-    const double inv1 = fast_rcp(piv1);
-    // (2) first pair's update on rows R+2, R+3 only:  x[c] += w_a tau_c - tau_a w_c
-    {
-      const double t2 = u[R + 2] * inv1, t3 = u[R + 3] * inv1, w2 = v[R + 2], w3 = v[R + 3];
-#pragma unroll
-      for (int q = (R + 2) / 32; q < (T::M + 31) / 32; ++q) {  // entries below R + 2 are dead
-        const int cc = lane + 32 * q;
-        if (cc >= R + 2 && cc < T::M) {
-          const double tc = u[cc] * inv1, wc = v[cc];
-          u2[cc] += w2 * tc - t2 * wc;
-          v2[cc] += w3 * tc - t3 * wc;
-        }
-      }
+    const double a = u[R + 1];
+    if (R + 2 >= m) {  // last pair on its own (m = 2 mod 4): nothing left to update, any pivot will do
+      pf *= a;
+      return m;
     }
-    __syncwarp();
-    const double piv2 = u2[R + 3];
-    const bool odd = tg & 1;
-    double af[MT], bf[MT];
-    if (!static_pivot_ok<T::M, BOUNDED>(piv2, u2, R + 3)) {
-      // second pivot rejected: commit the first pair alone (rank-2 update with both K halves carrying it) and stop
-      const double sa = odd ? -0.5 * inv1 : 0.5, sb = odd ? 1.0 : inv1;
-      const double* srcA = (odd ? u : v) + gr;
-      const double* srcB = (odd ? v : u) + gr;
-#pragma unroll
-      for (int t = TR; t < MT; ++t) {
-        af[t] = sa * srcA[8 * t];
-        bf[t] = sb * srcB[8 * t];
-      }
-      if (gr <= ((R + 1) & 7)) af[TR] = bf[TR] = 0.0;
-      tiles_update_from<MT, SR, TR>(c, sm, af, bf);
-      __syncwarp();
-      return R + 2;
-    }
-    pf *= piv2;
+    // (2) block pivot
+    const double2 bc = *reinterpret_cast<const double2*>(u + R + 2);
+    const double2 de = *reinterpret_cast<const double2*>(v + R + 2);
+    const double f = u2[R + 3];
+    const double q = fma(a, f, fma(bc.y, de.x, -bc.x * de.y));
+    // guard: growth of the update  ||r||^2 ||B^-1|| / s  <=  s sB / |q|  <=  kStaticBlockGrowth
+    const double sB = fabs(a) + fabs(bc.x) + fabs(bc.y) + fabs(de.x) + fabs(de.y) + fabs(f);  // >= max |B entry|
+    double s = 2.0;
+    if constexpr (!BOUNDED)
+      s = __hiloint2double((int)static_rows_max_key<T::M>(scratch, R) + 0x100, 0);  // >= max |entry| of the four rows
+    const bool ok = fabs(q) * (PHYSICAL ? kStaticBlockGrowthPhysical : kStaticBlockGrowth) >= s * sB && q != 0.0;
+    if (!ok) return R;
+    pf *= q;
     if (R + 4 >= m) return m;
-    const double inv2 = fast_rcp(piv2);
-    // (3) fragments: lane tg reads vector {w, u, w', u'}[tg] for A and {u, w, u', w'}[tg] for B
-    const double sa = odd ? ((tg & 2) ? -inv2 : -inv1) : 1.0;
-    const double sb = odd ? 1.0 : ((tg & 2) ? inv2 : inv1);
-    const int ka = tg ^ 1;
-    const double* srcA = scratch + (((ka & 1) << 1) | (ka >> 1)) * VS + gr;
-    const double* srcB = scratch + (((tg & 1) << 1) | (tg >> 1)) * VS + gr;
+    const double invq = fast_rcp(q);
+    // (3) fragments: A = row R + tg, B = y_tg = sum_j coef_j * row_j
+    const double k0 = L.y_ent[0][R] * (L.y_sgn[0] * invq), k1 = L.y_ent[1][R] * (L.y_sgn[1] * invq),
+                 k2 = L.y_ent[2][R] * (L.y_sgn[2] * invq);
+    constexpr int TI0 = (D & 1) ? TR + 1 : TR;  // tile row TR is dead once its second quadruple has been eliminated
+    double af[MT], bf[MT];
 #pragma unroll
-    for (int t = TR; t < MT; ++t) {
-      af[t] = sa * srcA[8 * t];
-      bf[t] = sb * srcB[8 * t];
+    for (int t = TI0; t < MT; ++t) {
+      af[t] = L.a_vec[8 * t];
+      bf[t] = fma(k0, L.y_vec[0][8 * t], fma(k1, L.y_vec[1][8 * t], k2 * L.y_vec[2][8 * t]));
     }
-    if (gr <= ((R + 3) & 7)) af[TR] = bf[TR] = 0.0;  // indices <= R+3 are dead: they neither change nor contribute
-    // (4) one DMMA per live upper tile; tile row TR is dead once its second quadruple has been eliminated
-    constexpr int TI0 = (D & 1) ? TR + 1 : TR;
+    if constexpr (!(D & 1)) {
+      if (gr <= ((R + 3) & 7)) af[TR] = bf[TR] = 0.0;  // indices <= R+3 are dead: they neither change nor contribute
+    }
+    // (4) one DMMA per live upper tile
     tiles_update_from<MT, SR, TI0>(c, sm, af, bf);
     __syncwarp();
-    return warp_pfaffian_static_steps<MT, SR, BOUNDED, D + 1>(c, m, scratch, sm, pf);
+    return warp_pfaffian_static_steps<MT, SR, BOUNDED, PHYSICAL, D + 1>(c, m, scratch, sm, pf, L);
   }
 }
 
 // c: fragments of the upper tiles (entries at rows/cols >= m must be 0); with SR > 0 the tiles of the first SR
 // tile-rows are read from / written to sm (this lane's slot, see tile_get) instead.  scratch: Tiles<MT>::kScratch
 // doubles private to the warp.  Returns the signed Pfaffian in every lane.
-template <int MT, int SR = 0, bool BOUNDED = false>
+template <int MT, int SR = 0, bool BOUNDED = false, bool PHYSICAL = BOUNDED>
 __device__ double warp_pfaffian_tiles(double (&c)[Tiles<MT>::NT][2], int m, double* scratch, double2* sm = nullptr) {
   if (m == 0) return 1.0;
   if (m & 1) return 0.0;
   double pf = 1.0;
-  const int done = warp_pfaffian_static_steps<MT, SR, BOUNDED>(c, m, scratch, sm, pf);
+  const StaticLane<MT> L = static_lane_setup<MT>(scratch);
+  const int done = warp_pfaffian_static_steps<MT, SR, BOUNDED, PHYSICAL>(c, m, scratch, sm, pf, L);
   if (done < m) pf *= warp_pfaffian_tiles_pivoted<MT, SR>(c, m, scratch, sm, done);
   return pf;
 }
