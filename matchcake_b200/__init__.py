@@ -4,8 +4,8 @@ Only the hot path is here: SPTM chaining, covariance conju
 Pfaffians, and the kernel Gram-matrix builder, as hand-written sm_100a CUDA behind the C ABI of
 ``include/mcb200.h``; plus the thin host-side mirror of the reference interface that calls it.
 """
-from . import _lib, observables, operations, ops, utils  # noqa: F401
+from . import _lib, observables, operations, ops, torch_ops, utils  # noqa: F401
 from .device import DeviceError, NIFDevice, NonInteractingFermionicDevice  # noqa: F401
-from . import ml, strategies  # noqa: F401
+from . import ml, pennylane_shell, star_state, strategies  # noqa: F401
 
 __version__ = "0.1.0"

@@ -24,6 +24,8 @@ from . import ops as _ops
 from .operations import (BasisState, CompRotation, CompZX, MatchgateOperation, Operation, ProductState,
                          SingleParticleTransitionMatrixOperation, SptmAngleEmbedding, SptmCompZX,
                          _SptmCompRotation, _as_f64_tensor, _wires_tuple, make_wires_continuous)
+from .pennylane_shell import PennyLaneDeviceMixin
+from .star_state import get_star_state_finding_strategy
 from .utils.jordan_wigner import JordanWigner, extend_majorana_indices
 
 _UNSET = object()
@@ -86,7 +88,7 @@ class _PauliStructureCache:
         return structure
 
 
-class NonInteractingFermionicDevice:
+class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
     name = "nif.qubit"
     R_DTYPE = torch.float64
     C_DTYPE = torch.complex128
@@ -145,6 +147,11 @@ class NonInteractingFermionicDevice:
         self.torch_device = torch.device(kwargs.get("device", "cuda"))
         self.output_device = kwargs.get("output_device", "cpu")
         self.show_progress = kwargs.get("show_progress", False)
+        #: highest-probability basis state search (nif_device.py:241-246): "Greedy" / "FromSampling" or an instance
+        self.star_state_finding_strategy = get_star_state_finding_strategy(
+            kwargs.get("star_state_finding_strategy", "FromSampling"))
+        self._star_state = None
+        self._star_probability = None
         self.apply_metadata: defaultdict = defaultdict()
         self._bits_cache: dict = {}
         self._circuit_cache: "OrderedDict[tuple, _ops.CompiledCircuit]" = OrderedDict()
@@ -192,9 +199,32 @@ class NonInteractingFermionicDevice:
         self._compiled = None
         self._batched = False
         self._samples = None
+        self._star_state = None
+        self._star_probability = None
         self.apply_metadata = defaultdict()
         if self._wires is not None:
             self._state_prep_op = self._default_state()
+
+    @property
+    def samples(self):
+        return self._samples
+
+    @property
+    def star_state(self):
+        """Highest-probability basis state of the last :meth:`compute_star_state` (nif_device.py:1243-1250)."""
+        return self._star_state
+
+    @property
+    def star_probability(self):
+        return self._star_probability
+
+    def compute_star_state(self, **kwargs) -> tuple:
+        """(star state, its probability) through ``star_state_finding_strategy`` (nif_device.py:489-504); the prefix
+        probabilities the strategies ask for are GPU read-outs (:meth:`get_states_probability`)."""
+        if self._star_state is None or self._star_probability is None:
+            self._star_state, self._star_probability = self.star_state_finding_strategy(
+                self, self.get_states_probability, show_progress=self.show_progress, samples=self._samples)
+        return self._star_state, self._star_probability
 
     def _default_state(self) -> ProductState:
         """|0..0> on the device wires (one immutable record per device, reused by every reset)."""
@@ -673,7 +703,12 @@ class NonInteractingFermionicDevice:
         return self._out(p if batched else p[0])
 
     def probability(self, wires=None, shot_range=None, bin_size=None):
-        return self.analytic_probability(wires=wires if wires is not None and len(_wires_tuple(wires)) else self.wires)
+        """Analytic marginal distribution without shots; relative frequencies of the recorded samples with shots
+        (nif_device.py:885-909)."""
+        wires = wires if wires is not None and len(_wires_tuple(wires)) else self.wires
+        if self._active_shots is None:
+            return self.analytic_probability(wires=wires)
+        return self._sampled_probability(_wires_tuple(wires), shot_range=shot_range, bin_size=bin_size)
 
     # ------------------------------------------------------------------ sampling
     def generate_samples(self, shots: Optional[int] = None, wires=None, seed: Optional[int] = None,
@@ -751,7 +786,10 @@ class NonInteractingFermionicDevice:
         return self._out(e if batched else e[0])
 
     def expval(self, observable, shot_range=None, bin_size=None):
-        return self.exact_expval(observable)
+        """Exact value without shots; sample mean over the recorded samples with shots (nif_device.py:679-703)."""
+        if self._active_shots is None:
+            return self.exact_expval(observable)
+        return self._sampled_expval(observable, shot_range=shot_range, bin_size=bin_size)
 
     # ------------------------------------------------------------------ execution
     def execute_generator(self, op_iterator: Iterable, observable: Optional[Any] = None,
@@ -779,12 +817,14 @@ class NonInteractingFermionicDevice:
             if self._samples is None:
                 self._samples = self.generate_samples()
             return self._samples
+        if self._active_shots is not None and self._samples is None:  # nif_device.py:667-668
+            self._samples = self.generate_samples()
         if output_type == "expval":
             return self.expval(observable)
         if output_type == "probs":
             return self.probability(wires=kwargs.get("wires", None))
         if output_type in ("star_state", "*state"):
-            raise NotImplementedError(f"Output type {output_type} (star-state search) is outside the B200 hot path.")
+            return self.compute_star_state(**kwargs)
         raise ValueError(f"Output type {output_type} is not supported.")
 
 
@@ -792,5 +832,19 @@ from .operations import (CompRxRx as _CRx, CompRyRy as _CRy, CompRzRz as _CRz, S
                          SptmCompRyRy as _SRy, SptmCompRzRz as _SRz)
 
 _FAST_OPS = frozenset({_CRx, _CRy, _CRz, _SRx, _SRy, _SRz, CompZX, SptmCompZX})
+
+
+def _all_subclasses(cls):
+    out = set()
+    for sub in cls.__subclasses__():
+        out.add(sub)
+        out |= _all_subclasses(sub)
+    return out
+
+
+# names the PennyLane decomposition stops at (nif_device.py:124-135)
+NonInteractingFermionicDevice._supported_ops = set(PennyLaneDeviceMixin._supported_ops) | {
+    c.__name__ for base in (MatchgateOperation, SingleParticleTransitionMatrixOperation, SptmAngleEmbedding, ProductState,
+                            BasisState) for c in ({base} | _all_subclasses(base))}
 
 NIFDevice = NonInteractingFermionicDevice

@@ -118,6 +118,39 @@ class FermionicPQCKernelOracle:
         return self.gram(x, self.x_train_, **kw)
 
 
+class LinearNIFKernelOracle(FermionicPQCKernelOracle):
+    """linear_nif_kernel.py:107-127: ``h[triu] = act(W x + b)``, ``h[tril] = -h^T``, ``R = matrix_exp(h)``; the Gram is
+    the NIFKernel one (per-pair ``R_i R_j^T`` through the lookup-table strategy).  The encoder weights are the caller's
+    (the reference draws them from torch's default Linear initialiser)."""
+
+    def __init__(self, n_qubits: int, weight: np.ndarray, bias: Optional[np.ndarray] = None,
+                 activation: str = "Identity", gram_batch_size: int = 10_000):
+        super().__init__(n_qubits, gram_batch_size=gram_batch_size)
+        self.weight = np.asarray(weight, dtype=np.float64)
+        self.bias = None if bias is None else np.asarray(bias, dtype=np.float64)
+        self.activation = {"Identity": lambda v: v, "Tanh": np.tanh, "ReLU": lambda v: np.maximum(v, 0.0)}[activation]
+
+    def fit(self, x_train, y_train=None):
+        self.x_train_ = np.asarray(x_train)
+        return self
+
+    def hamiltonian(self, x: np.ndarray) -> np.ndarray:
+        x = np.asarray(x, dtype=np.float64).reshape(len(x), -1)
+        out = x @ self.weight.T + (0.0 if self.bias is None else self.bias)
+        d = 2 * self.n_qubits
+        h = np.zeros((len(x), d, d))
+        iu = np.triu_indices(d, k=1)
+        h[:, iu[0], iu[1]] = self.activation(out)
+        il = np.tril_indices(d, k=-1)
+        h[:, il[0], il[1]] = -1.0 * h[:, il[1], il[0]]
+        return h
+
+    def x_to_sptm(self, x: np.ndarray) -> np.ndarray:
+        from scipy.linalg import expm
+
+        return np.stack([expm(hi) for hi in self.hamiltonian(x)])
+
+
 def indices_batch_generator(shape: Tuple[int, int], batch_size: int = 32) -> Iterator[np.ndarray]:
     """gram_matrix.py:177-201 (vectorised; same cells, same row-major order)."""
     n0, n1 = shape

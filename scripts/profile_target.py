@@ -1,4 +1,4 @@
-"""Small single-GPU targets for ncu: python scripts/profile_target.py {c2|gram|c4|pf} [size]"""
+"""Small single-GPU targets for ncu: python scripts/profile_target.py {c2|gram|c4|blocks|matmul|pf} [size]"""
 import sys
 
 import numpy as np
@@ -46,6 +46,14 @@ elif what == "blocks":
     b1 = torch.randn(4096, 64, 6, dtype=torch.float64, device=dev)
     for _ in range(2):
         out = mops.gram_blocks4(b0, b1)
+elif what == "matmul":
+    # dense SPTM chaining (K1 dense): sptm_matmul_tma_kernel for n <= 64, bgemm_dmma_kernel above
+    n = size or 64
+    B = max(256, (1 << 26) // (n * n))  # 512 MB per operand: larger than L2
+    a = torch.randn(B, n, n, dtype=torch.float64, device=dev)
+    b = torch.randn_like(a)
+    for _ in range(3):
+        out = mops.sptm_matmul(a, b)
 elif what == "pf":
     m = size or 64
     a = torch.randn(20000, m, m, dtype=torch.float64, device=dev)
