@@ -375,7 +375,7 @@ def build_workload(name: str, ctx: Ctx):
             return rel
 
         w.update(step=step, e2e_step=e2e_step, units=B * ws, e2e_units=B * ws, metric="circuit_expvals_per_sec",
-                 unit="expvals/s", scaling="weak", kernel="expval_warp_kernel<4>",
+                 unit="expvals/s", scaling="weak", kernel="expval_cov_kernel<4>",
                  flops_per_launch=c2_flops_per_unit(n) * B, launches_per_step=1, h2d=B * 2 * 8, d2h=B * 8,
                  parity=parity, dominant=None, e2e_api="NonInteractingFermionicDevice.execute_generator (pinned host "
                  "parameters in, host tensor out)")
@@ -563,13 +563,8 @@ def build_workload(name: str, ctx: Ctx):
         layout = [(op_cls[l % 3], q) for l in range(depth) for q in range(l % 2, n - 1, 2)]
 
         def e2e_step(i):
-            if hasattr(qdev, "execute_layered"):
-                last["e2e_out"] = qdev.execute_layered(layout, host_params, probs_wires=list(range(k)))
-                return last["e2e_out"]
-            p = host_params.to(dev, non_blocking=True).view(B, len(layout), 2)
-            ops_ = [cls(p[:, j], wires=[q, q + 1]) for j, (cls, q) in enumerate(layout)]
-            qdev.execute_generator(ops_, reset=True)
-            last["e2e_out"] = qdev.analytic_probability(list(range(k)))
+            # one (B, P) parameter tensor + gate layout; H2D chunks double-buffered against the kernels (device.py)
+            last["e2e_out"] = qdev.execute_layered(layout, host_params, probs_wires=list(range(k)))
             return last["e2e_out"]
 
         def parity():
@@ -592,7 +587,8 @@ def build_workload(name: str, ctx: Ctx):
                  flops_per_launch=len(gates) * 12 * (2 * k) * B, launches_per_step=None, h2d=B * off * 8,
                  d2h=B * (2 ** k) * 8, parity=parity,
                  dominant=lambda: (lambda: mops.circuit_columns(circ, params, maj)),
-                 e2e_api="NonInteractingFermionicDevice (pinned host parameters in, host probabilities out)",
+                 e2e_api="NonInteractingFermionicDevice.execute_layered (pinned host parameters streamed in chunks, "
+                 "host probabilities out)",
                  hbm_bytes_per_launch=B * off * 8 + B * 2 * n * 2 * k * 8)
     return w
 

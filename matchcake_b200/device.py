@@ -803,6 +803,122 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
             self.apply_generator(op_iterator, **kwargs)
         return self.execute_output(observable=observable, output_type=output_type, shots=shots, **kwargs)
 
+    # ------------------------------------------------------------------ layered circuits, streamed parameters
+    def _layered_circuit(self, layout) -> "_ops.CompiledCircuit":
+        """Circuit descriptor of a gate layout ``[(op class, wires | wire0), ...]`` (application order): rotation gates
+        take two consecutive parameter columns each, in layout order; fSWAPs none.  Cached per layout."""
+        key = ("layered", tuple((cls, w if isinstance(w, (int, np.integer)) else tuple(w)) for cls, w in layout),
+               self._wires)
+        circ = self._circuit_cache.get(key)
+        if circ is not None:
+            self._circuit_cache.move_to_end(key)
+            return circ
+        gates, off = [], 0
+        for cls, w in layout:
+            wires = (w, w + 1) if isinstance(w, (int, np.integer)) else tuple(w)
+            idx = tuple(self._wire_index(x) for x in wires)
+            if issubclass(cls, (CompRotation, _SptmCompRotation)):
+                gates.append(_ops.GateSpec(cls.GATE_KIND, idx[0], idx[1], off))
+                off += 2
+            elif issubclass(cls, (CompZX, SptmCompZX)):
+                lo, hi = min(idx), max(idx)
+                gates.append(_ops.GateSpec(_ops.GATE_FSWAP, lo, hi, 0, _ops.FLAG_TRANSPOSE if idx[0] != lo else 0))
+            else:
+                raise DeviceError(f"execute_layered handles rotation gates and fSWAPs; got {cls.__name__}. Use "
+                                  f"execute_generator for general operation streams.")
+        circ = _ops.CompiledCircuit(self.num_wires, gates, off, device=self.torch_device)
+        self._circuit_cache[key] = circ
+        while len(self._circuit_cache) > 16:
+            self._circuit_cache.popitem(last=False)
+        return circ
+
+    def execute_layered(self, layout, params, probs_wires=None, observable=None, chunk_rows: Optional[int] = None):
+        """Deep parametrised circuits without per-gate Python objects: ``layout`` = ``[(op class, wires), ...]`` in
+        application order and ONE parameter tensor ``params`` (B, 2 * n_rotation_gates) -- the same circuit
+        ``apply_generator`` would record from ``cls(params[:, 2j:2j+2], wires)`` objects (nif_device.py:281-347), the
+        read-out of ``analytic_probability`` (:430-479, ``probs_wires``) or of a basis-state projector ``observable``.
+
+        Host-resident parameters (pinned memory) are streamed: the batch is cut into chunks, the host->device copy of
+        chunk c+1 runs on a copy stream while the kernels of chunk c run on the current stream (two device buffers),
+        and each chunk's result is copied back on a third stream, so the call costs about one pass of the parameters
+        over PCIe instead of copy + compute + copy."""
+        if (probs_wires is None) == (observable is None):
+            raise ValueError("execute_layered needs exactly one of probs_wires / observable")
+        if self._state_prep_op is None or not self._is_basis_input():
+            raise DeviceError("execute_layered starts from a computational basis state")
+        circ = self._layered_circuit(layout)
+        n = self.num_wires
+        if not isinstance(params, torch.Tensor):
+            params = torch.as_tensor(np.asarray(params))
+        if params.ndim != 2 or params.shape[1] != circ.n_param_cols:
+            raise ValueError(f"params must have shape (B, {circ.n_param_cols}), got {tuple(params.shape)}")
+        B = params.shape[0]
+        dev = self.torch_device
+        bits = self._bits_device(self._state_prep_op.basis_state_bits())
+        if probs_wires is not None:
+            widx = np.array([self._wire_index(w) for w in _wires_tuple(probs_wires)], dtype=int)
+            k = len(widx)
+            target = None
+        else:
+            if not _is_projector(observable):
+                raise DeviceError("execute_layered reads out probabilities or a basis-state projector")
+            widx = np.array([self._wire_index(w) for w in observable.wires], dtype=int)
+            k = len(widx)
+            target = self._bits_device(np.asarray(observable.parameters[0]).astype(np.int8).reshape(1, k))
+        maj = torch.as_tensor(np.stack([2 * widx, 2 * widx + 1], axis=1).ravel().astype(np.int32), device=dev)
+        floor2 = self._floor2(k)
+        width = (1 << k) if target is None else 1
+
+        def read_out(p_dev: torch.Tensor) -> torch.Tensor:
+            cov = _ops.cov_basis(_ops.circuit_columns(circ, p_dev, maj), n, bits)
+            if target is None:
+                return _ops.probs_all(cov, normalize=True, floor2=floor2)
+            return _ops.probs(cov, target, floor2=floor2)
+
+        self._batched = True
+        if params.is_cuda:
+            out = read_out(params.to(torch.float64))
+            return self._out(out if target is None else out[:, 0])
+
+        params = params.to(torch.float64)
+        if not params.is_pinned():
+            params = params.pin_memory()
+        row_bytes = max(1, params.shape[1] * 8)
+        rows = chunk_rows or max(256, min(B, (32 << 20) // row_bytes))      # ~32 MB per copy
+        main = torch.cuda.current_stream(dev)
+        copy_in, copy_out = self._side_streams()
+        host_out = torch.empty((B, width), dtype=torch.float64, pin_memory=True)
+        bufs = [torch.empty((min(rows, B), params.shape[1]), dtype=torch.float64, device=dev) for _ in range(2)]
+        free = [None, None]          # event: kernels that read bufs[i] are done
+        copy_in.wait_stream(main)
+        copy_out.wait_stream(main)
+        for c, s in enumerate(range(0, B, rows)):
+            e = min(B, s + rows)
+            buf = bufs[c & 1][: e - s]
+            with torch.cuda.stream(copy_in):
+                if free[c & 1] is not None:
+                    copy_in.wait_event(free[c & 1])
+                buf.copy_(params[s:e], non_blocking=True)
+                ready = copy_in.record_event()
+            main.wait_event(ready)
+            res = read_out(buf)
+            free[c & 1] = main.record_event()
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(free[c & 1])
+                host_out[s:e].copy_(res, non_blocking=True)
+                res.record_stream(copy_out)
+        copy_out.synchronize()
+        main.wait_stream(copy_in)
+        out = host_out if target is None else host_out[:, 0]
+        out = out.to(self.R_DTYPE)
+        return out if self.output_device in (None, "cpu") else out.to(self.output_device)
+
+    def _side_streams(self):
+        st = getattr(self, "_streams", None)
+        if st is None:
+            st = self._streams = (torch.cuda.Stream(self.torch_device), torch.cuda.Stream(self.torch_device))
+        return st
+
     def execute_output(self, observable: Optional[Any] = None, output_type: Optional[str] = None, *,
                        shots: Any = _UNSET, **kwargs):
         if output_type is None:

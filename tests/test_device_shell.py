@@ -376,3 +376,47 @@ def test_linear_nif_kernel_encoder_is_trainable_through_the_adjoint_kernels():
         down = float(k(x).double().sum())
         w[2, 1] += eps
     assert abs((up - down) / (2 * eps) - float(w.grad[2, 1])) < 1e-6 * max(1.0, abs(float(w.grad[2, 1])))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host", [True, False])
+def test_execute_layered_equals_the_op_stream(host):
+    """One (B, P) parameter tensor + layout == the same circuit given as operation objects, for streamed host parameters
+    (several chunks, ragged last chunk) and for device-resident ones; probabilities and projector read-out."""
+    n, depth, B, k = 10, 6, 37, 3
+    rng = np.random.default_rng(5)
+    classes = (SptmCompRxRx, SptmCompRyRy, CompRzRz)
+    layout = []
+    for l in range(depth):
+        for q in range(l % 2, n - 1, 2):
+            layout.append((classes[l % 3], q))
+        if l == 2:
+            layout.append((SptmFSwap, (7, 2)))
+            layout.append((fSWAP, (4, 5)))
+    n_rot = sum(1 for cls, _ in layout if cls not in (SptmFSwap, fSWAP))
+    params = rng.uniform(0, 2 * np.pi, (B, 2 * n_rot))
+    dev = mc.NIFDevice(n)
+    p_in = torch.as_tensor(params).pin_memory() if host else torch.as_tensor(params).cuda()
+    got = dev.execute_layered(layout, p_in, probs_wires=[0, 4, 9], chunk_rows=8 if host else None)
+    stream, j = [], 0
+    for cls, w in layout:
+        if cls in (SptmFSwap, fSWAP):
+            stream.append(cls(wires=list(w)))
+        else:
+            stream.append(cls(params[:, 2 * j:2 * j + 2], wires=[w, w + 1]))
+            j += 1
+    ref_dev = mc.NIFDevice(n)
+    ref_dev.execute_generator(stream, reset=True)
+    ref = ref_dev.analytic_probability([0, 4, 9])
+    assert got.shape == (B, 8) and got.device.type == "cpu"
+    np.testing.assert_array_equal(got.numpy(), ref.numpy())
+    tgt = np.array([1, 0, 1, 1])
+    proj = obs.Projector(tgt, wires=[2, 3, 5, 8])
+    got_e = dev.execute_layered(layout, p_in, observable=proj, chunk_rows=16 if host else None)
+    np.testing.assert_array_equal(got_e.numpy(), ref_dev.expval(proj).numpy())
+    with pytest.raises(ValueError):
+        dev.execute_layered(layout, p_in[:, :-2], probs_wires=[0])
+    with pytest.raises(ValueError):
+        dev.execute_layered(layout, p_in)
+    with pytest.raises(mc.DeviceError):
+        dev.execute_layered([(MatchgateOperation, 0)], p_in, probs_wires=[0])
