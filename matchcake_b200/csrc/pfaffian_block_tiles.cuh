@@ -58,6 +58,108 @@ __device__ __forceinline__ void bt_update(double2* tiles, int MT, int ti0, const
   }
 }
 
+// Pivoted continuation (Parlett-Reid with logical pivoting) on the indices >= done of the matrix held in `tiles`
+// (packed upper tiles of an MT-tile-row matrix); pf = product of the pivots taken so far.  Returns the signed Pfaffian,
+// valid in every thread; ends with a block barrier.  Needs vec = 4 * (MAXM + 4) doubles, m <= MAXM <= blockDim.x.
+template <int MAXM>
+__device__ double bt_pivoted_tail(double2* tiles, int MT, int m, int done, double* vec, double pf) {
+  constexpr int kBtMaxM = MAXM, kBtVS = MAXM + 4, kWords = MAXM / 32;
+  const int tid = threadIdx.x, lane = tid & 31, gr = lane >> 2, tg = lane & 3;
+  double* u = vec;
+  double* v = vec + 2 * kBtVS;
+  double* u2 = vec + kBtVS;
+  double* v2 = vec + 3 * kBtVS;
+  // ---- pivoted continuation on the indices >= done
+  if (done < m) {
+    __syncthreads();
+    unsigned act[kWords];
+#pragma unroll
+    for (int q = 0; q < kWords; ++q) {
+      const int lo = 32 * q, hi = lo + 32;
+      unsigned bits = 0u;
+      if (m > lo) bits = (m >= hi) ? 0xffffffffu : ((1u << (m - lo)) - 1u);
+      if (done > lo) bits &= (done >= hi) ? 0u : ~((1u << (done - lo)) - 1u);
+      act[q] = bits;
+    }
+    auto is_act = [&](int c) { return (act[c >> 5] >> (c & 31)) & 1u; };
+    unsigned parity = 0;
+    double* rowbuf = u;   // A[r][c]
+    double* colbuf = v;   // A[c][p]
+    double* tauv = u2;    // tau
+    double* vv = v2;      // v
+    const int steps = (m - done) >> 1;
+    for (int s = 0; s < steps; ++s) {
+      int r = 0;
+#pragma unroll
+      for (int q = kWords - 1; q >= 0; --q)
+        if (act[q]) r = 32 * q + __ffs((int)act[q]) - 1;
+      act[r >> 5] &= ~(1u << (r & 31));
+      if (tid < kBtMaxM) rowbuf[tid] = (tid < m && is_act(tid)) ? bt_elem(tiles, MT, r, tid) : 0.0;
+      __syncthreads();
+      // pivot: largest |A[r][c]| over the active c (first index among equals)
+      unsigned key = 0u;
+      int bj = 0;
+#pragma unroll
+      for (int q = 0; q < kBtMaxM / 32; ++q) {
+        const int c = lane + 32 * q;
+        const unsigned k2 = (unsigned)__double2hiint(rowbuf[c]) & 0x7fffffffu;
+        if (k2 > key) {
+          key = k2;
+          bj = c;
+        }
+      }
+      const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+      if (kmax == 0u) {  // singular
+        pf = 0.0;
+        break;
+      }
+      const unsigned cand = (key == kmax) ? (unsigned)bj : 0xffffffffu;
+      const int p = (int)__reduce_min_sync(0xffffffffu, cand);
+      const double piv = rowbuf[p];
+      // sign: active indices strictly between r and p (r is already cleared)
+      {
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < kWords; ++q) {
+          unsigned mask = act[q];
+          const int lo = 32 * q;
+          if (p <= lo) mask = 0u;
+          else if (p < lo + 32) mask &= (1u << (p - lo)) - 1u;
+          if (r >= lo + 31) mask = 0u;
+          else if (r >= lo) mask &= ~((2u << (r - lo)) - 1u);
+          cnt += __popc(mask);
+        }
+        parity ^= (unsigned)cnt;
+      }
+      act[p >> 5] &= ~(1u << (p & 31));
+      pf *= piv;
+      if (s == steps - 1) break;
+      const double inv = fast_rcp(piv);
+      if (tid < kBtMaxM) {
+        const bool on = tid < m && is_act(tid);
+        colbuf[tid] = on ? bt_elem(tiles, MT, tid, p) : 0.0;
+      }
+      __syncthreads();
+      if (tid < kBtMaxM) {
+        const double t = rowbuf[tid] * inv;  // 0 on inactive entries (p itself was cleared above -> mask it here)
+        const bool on = tid < m && is_act(tid);
+        tauv[tid] = on ? t : 0.0;
+        vv[tid] = on ? colbuf[tid] : 0.0;
+      }
+      __syncthreads();
+      // A += tau v^T - v tau^T: A-fragment columns (tau/2, -v/2, tau/2, -v/2), B-fragment rows (v; tau; v; tau)
+      {
+        const bool odd = tg & 1;
+        bt_update(tiles, MT, 0, (odd ? vv : tauv) + gr, odd ? -0.5 : 0.5, (odd ? tauv : vv) + gr, 1.0, -1);
+      }
+      __syncthreads();
+    }
+    if (parity & 1u) pf = -pf;
+  }
+  __syncthreads();
+  return pf;
+}
+
 // Signed Pfaffian of matrix `item` of `src` (m <= MAXM), computed by the whole block of MAXM threads; the result is
 // valid in every thread.  tiles: MT(MT+1)/2 * 32 double2 (shared or global), vec: 4 * (MAXM + 4) doubles of shared
 // memory.  Ends with a block barrier.
@@ -130,96 +232,37 @@ __device__ double block_tiles_pfaffian(const Src& src, long long item, int m, do
                 vec + (((tg & 1) << 1) | (tg >> 1)) * kBtVS + gr, odd ? 1.0 : ((tg & 2) ? inv2 : inv1), R + 3);
       __syncthreads();
     }
-    // ---- pivoted continuation on the indices >= done
-    if (done < m) {
-      __syncthreads();
-      unsigned act[kWords];
-#pragma unroll
-      for (int q = 0; q < kWords; ++q) {
-        const int lo = 32 * q, hi = lo + 32;
-        unsigned bits = 0u;
-        if (m > lo) bits = (m >= hi) ? 0xffffffffu : ((1u << (m - lo)) - 1u);
-        if (done > lo) bits &= (done >= hi) ? 0u : ~((1u << (done - lo)) - 1u);
-        act[q] = bits;
-      }
-      auto is_act = [&](int c) { return (act[c >> 5] >> (c & 31)) & 1u; };
-      unsigned parity = 0;
-      double* rowbuf = u;   // A[r][c]
-      double* colbuf = v;   // A[c][p]
-      double* tauv = u2;    // tau
-      double* vv = v2;      // v
-      const int steps = (m - done) >> 1;
-      for (int s = 0; s < steps; ++s) {
-        int r = 0;
-#pragma unroll
-        for (int q = kWords - 1; q >= 0; --q)
-          if (act[q]) r = 32 * q + __ffs((int)act[q]) - 1;
-        act[r >> 5] &= ~(1u << (r & 31));
-        if (tid < kBtMaxM) rowbuf[tid] = (tid < m && is_act(tid)) ? bt_elem(tiles, MT, r, tid) : 0.0;
-        __syncthreads();
-        // pivot: largest |A[r][c]| over the active c (first index among equals)
-        unsigned key = 0u;
-        int bj = 0;
-#pragma unroll
-        for (int q = 0; q < kBtMaxM / 32; ++q) {
-          const int c = lane + 32 * q;
-          const unsigned k2 = (unsigned)__double2hiint(rowbuf[c]) & 0x7fffffffu;
-          if (k2 > key) {
-            key = k2;
-            bj = c;
-          }
-        }
-        const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
-        if (kmax == 0u) {  // singular
-          pf = 0.0;
-          break;
-        }
-        const unsigned cand = (key == kmax) ? (unsigned)bj : 0xffffffffu;
-        const int p = (int)__reduce_min_sync(0xffffffffu, cand);
-        const double piv = rowbuf[p];
-        // sign: active indices strictly between r and p (r is already cleared)
-        {
-          int cnt = 0;
-#pragma unroll
-          for (int q = 0; q < kWords; ++q) {
-            unsigned mask = act[q];
-            const int lo = 32 * q;
-            if (p <= lo) mask = 0u;
-            else if (p < lo + 32) mask &= (1u << (p - lo)) - 1u;
-            if (r >= lo + 31) mask = 0u;
-            else if (r >= lo) mask &= ~((2u << (r - lo)) - 1u);
-            cnt += __popc(mask);
-          }
-          parity ^= (unsigned)cnt;
-        }
-        act[p >> 5] &= ~(1u << (p & 31));
-        pf *= piv;
-        if (s == steps - 1) break;
-        const double inv = fast_rcp(piv);
-        if (tid < kBtMaxM) {
-          const bool on = tid < m && is_act(tid);
-          colbuf[tid] = on ? bt_elem(tiles, MT, tid, p) : 0.0;
-        }
-        __syncthreads();
-        if (tid < kBtMaxM) {
-          const double t = rowbuf[tid] * inv;  // 0 on inactive entries (p itself was cleared above -> mask it here)
-          const bool on = tid < m && is_act(tid);
-          tauv[tid] = on ? t : 0.0;
-          vv[tid] = on ? colbuf[tid] : 0.0;
-        }
-        __syncthreads();
-        // A += tau v^T - v tau^T: A-fragment columns (tau/2, -v/2, tau/2, -v/2), B-fragment rows (v; tau; v; tau)
-        {
-          const bool odd = tg & 1;
-          bt_update(tiles, MT, 0, (odd ? vv : tauv) + gr, odd ? -0.5 : 0.5, (odd ? tauv : vv) + gr, 1.0, -1);
-        }
-        __syncthreads();
-      }
-      if (parity & 1u) pf = -pf;
-    }
+    if (done < m) return bt_pivoted_tail<MAXM>(tiles, MT, m, done, vec, pf);
     __syncthreads();
     return pf;
   }
 }
+
+// Gram cells for 64 < d <= 256: one block per evaluated cell (i, j), matrix cov0[i] + cov1[j] (gram_matrix.py rules as in
+// the other Gram kernels: only i > j, or j > i when n0 < n1, unless FULL; REFERENCE mirrors the value).
+struct GramPairSrc {
+  const double* a;
+  const double* b;
+  int m;
+  __device__ __forceinline__ double at(long long, int i, int j) const {
+    if (i >= m || j >= m || i == j) return 0.0;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    const double v = a[lo * m + hi] + b[lo * m + hi];
+    return i < j ? v : -v;
+  }
+};
+
+struct GramBtArgs {
+  const double* cov0;
+  const double* cov1;
+  long long n0, n1;
+  int d;
+  long long row_begin, rows;
+  int mode;
+  double scale;
+  double* K;
+  long long ldk;
+  double floor2;
+};
 
 }  // namespace mcb200

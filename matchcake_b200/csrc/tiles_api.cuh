@@ -26,6 +26,13 @@ int block_tiles_pfaffian_sector(const double* cov, long long B, int D, const int
 int block_tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
                      long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,
                      cudaStream_t st);
+// 128 < m <= 256, panel-blocked (pfaffian_panel.cu): first 128 indices eliminated in shared memory, Schur complement as
+// one K = 128 DMMA product, remainder by the m <= 128 routine; the workspace only backs the pivoted fallback
+long long panel_workspace_bytes(long long n_items, int m);
+int panel_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out, void* workspace,
+                         cudaStream_t st);
+int panel_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
+               long long row_end, int mode, double scale, double* K, long long ldk, void* workspace, cudaStream_t st);
 long long tiles_gram_workspace_bytes(long long n0, long long n1, int d);
 int tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
                long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,

@@ -54,6 +54,16 @@ elif what == "matmul":
     b = torch.randn_like(a)
     for _ in range(3):
         out = mops.sptm_matmul(a, b)
+elif what == "pfcov":  # Pfaffians of Lambda_i + Lambda_j (what the Gram path feeds K3)
+    m = size or 256
+    ns, n = 256, 8000
+    r = torch.linalg.qr(torch.randn(ns, m, m, dtype=torch.float64, device=dev))[0]
+    cov = mops.cov_basis(r.contiguous(), m // 2)
+    i = torch.randint(0, ns, (n,), device=dev)
+    j = (i + 1 + torch.randint(0, ns - 1, (n,), device=dev)) % ns
+    a = cov[i] + cov[j]
+    for _ in range(3):
+        out = mops.pfaffian(a)
 elif what == "pf":
     m = size or 64
     a = torch.randn(20000, m, m, dtype=torch.float64, device=dev)

@@ -33,7 +33,7 @@ def compiled(ops, n, batch, **kw):
 
 
 # ------------------------------------------------------------------ K3
-@pytest.mark.parametrize("m", [2, 4, 6, 8, 16, 30, 32, 34, 62, 64, 66, 96, 128, 130, 256])
+@pytest.mark.parametrize("m", [2, 4, 6, 8, 16, 30, 32, 34, 62, 64, 66, 96, 128, 130, 136, 146, 200, 250, 256])
 @pytest.mark.parametrize("signed", [True, False])
 def test_pfaffian_matches_oracle(m, signed):
     from matchcake_b200 import ops as mops
