@@ -206,6 +206,55 @@ def cpu_c3(seconds, nsub=128):
             f"{reps} x {len(idx)} Gram cells of a {nsub}-sample sub-Gram of the c3 kernel ({dt:.1f} s)")
 
 
+def cpu_c4(seconds, batch=64):
+    """numpy oracle of config C4 (dense per-layer chain, complex lookup-table read-out of the 256 outcomes)."""
+    from oracle import covariance as cv
+    from oracle import gates as og
+    from oracle import readout
+
+    n, depth, k = 64, 64, 8
+    rng = np.random.default_rng(1)
+    knames = ("CompRxRx", "CompRyRy", "CompRzRz")
+    amp = cv.amplitudes_from_basis_state(np.zeros(n, int))
+
+    def step():
+        ops_ = [og.Op(knames[l % 3], (q, q + 1), params=rng.uniform(0, 2 * np.pi, (batch, 2)))
+                for l in range(depth) for q in range(l % 2, n - 1, 2)]
+        return readout.analytic_probability(og.chain(ops_, n), amp, list(range(k)))
+
+    t0 = time.perf_counter()
+    reps = 0
+    while reps == 0 or time.perf_counter() - t0 < seconds:
+        step()
+        reps += 1
+    dt = time.perf_counter() - t0
+    return batch * reps / dt, os.cpu_count() or 1, f"{reps} x {batch} instances of the c4 circuit, numpy oracle ({dt:.1f} s)"
+
+
+def cpu_c5(seconds, nf, nsub=6):
+    """Per-pair reference path at N = 128 (dense R_i R_j^T, complex lookup table, 256 x 256 complex determinant): the
+    reference has no block factorisation, so c5 (nf = 128) and c5c (nf = 256) cost the same per cell."""
+    import torch
+
+    from oracle import kernels as okern
+    from oracle import ref_torch
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    xs = np.random.default_rng(1).random((nsub, nf))
+    ko = okern.FermionicPQCKernelOracle(n_qubits=128, rotations="X,Z").fit(xs)
+    s = ko.x_to_sptm(xs)
+    idx = np.stack(np.tril_indices(nsub, -1), axis=1)
+    ref_torch.gram_pairs(s, s, idx[:4])
+    t0 = time.perf_counter()
+    reps = 0
+    while reps == 0 or time.perf_counter() - t0 < seconds:
+        ref_torch.gram_pairs(s, s, idx)
+        reps += 1
+    dt = time.perf_counter() - t0
+    return (len(idx) * reps / dt, torch.get_num_threads(),
+            f"{reps} x {len(idx)} Gram cells of a {nsub}-sample sub-Gram at N=128, {nf} features ({dt:.1f} s)")
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's CPU op sequence (oracle/ref_torch.py) on the host cores, same metric / unit / config as ours.
@@ -267,7 +316,17 @@ def run_reference(args):
                           "data": "synthetic", "config": g["config"], "cpu_baseline": g["cpu_baseline"],
                           "e2e": g["e2e"], "note": note}))
     else:
-        print(json.dumps({"impl": "reference", "unavailable": f"no CPU arm for workload {args.workload}"}))
+        leg = {"c4": lambda: cpu_c4(10.0), "c5": lambda: cpu_c5(10.0, 128), "c5c": lambda: cpu_c5(10.0, 256)}[args.workload]
+        val, used, sample = leg()
+        metric, unit = (("marginal_distributions_per_sec", "distributions/s") if args.workload == "c4"
+                        else ("gram_entries_per_sec", "entries/s"))
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
+                          "steps": 1, "warmup": 0, "ms_per_step": None, "higher_is_better": True,
+                          "scaling": "weak" if args.workload == "c4" else "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic", "config": config_for(args.workload, ws),
+                          "cpu_baseline": {"value": val, "unit": unit, "cores": used, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "note": note}))
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -492,6 +551,19 @@ def build_workload(name: str, ctx: Ctx):
         tri = nl * (nl - 1) // 2
         rect = ns * nl - nl * (nl + 1) // 2
         entries = (tri if name == "c5" else 0) + rect
+        e2e_step = None
+        if name == "c5c":
+            # end to end through the kernel's public call: pinned host features in, Gram read back to pinned host memory.
+            # (c5 has no e2e leg: its 262144 x 4096 float64 output is 8.6 GB per step -- Nystroem.transform keeps it
+            # row-sharded on the devices and only the (n, 4096) embedding leaves them.)
+            x_host, basis_host = torch.as_tensor(x).pin_memory(), torch.as_tensor(basis).pin_memory()
+            out_host = torch.empty((ns, nl), dtype=torch.float64).pin_memory() if rank == 0 else None
+
+            def e2e_step(i):
+                k = kern(x_host, basis_host)
+                if rank == 0:
+                    out_host.copy_(k)
+                return out_host
 
         def parity():
             from oracle import kernels as okern
@@ -507,9 +579,30 @@ def build_workload(name: str, ctx: Ctx):
             o = okern.FermionicPQCKernelOracle(n_qubits=n, rotations="X,Z").fit(x[:8])
             ui, inv_i = np.unique(ii, return_inverse=True)
             uj, inv_j = np.unique(jj, return_inverse=True)
-            ref = o.pair_expvals(o.x_to_sptm(x[ui]), o.x_to_sptm(basis[uj]), np.stack([inv_i, inv_j], axis=1))
+            s0, s1 = o.x_to_sptm(x[ui]), o.x_to_sptm(basis[uj])
+            pairs = np.stack([inv_i, inv_j], axis=1)
+            ref = o.pair_expvals(s0, s1, pairs)
             got = loc[torch.as_tensor(ii - s, device=dev), torch.as_tensor(jj, device=dev)].cpu().numpy()
-            return parity_max_rel(got, ref, atol=0.0)
+            rel = parity_max_rel(got, ref, atol=0.0)
+            # At N = 128 the entries (1e-17 .. 1e-20) sit below the reference's floor sqrt(K^2 + 1e-32), which both sides
+            # apply: the comparison above is dominated by it.  Also compare the EXACT |Pf| (floor off, same kernels,
+            # rank-local launch) of the same cells with the oracle's log-determinant.
+            from oracle import lookup_table as lt
+
+            zeros = np.zeros(n, dtype=int)
+            r = np.einsum("pij,pkj->pik", s0[pairs[:, 0]], s1[pairs[:, 1]])
+            obs = lt.observable_matrix(lt.transition_matrix(r), zeros, zeros, np.arange(n))
+            obs = obs.reshape((-1,) + obs.shape[-2:])
+            exact_ref = np.exp(0.5 * np.linalg.slogdet(obs)[1])
+            xs, bs = torch.as_tensor(x[ui]).to(dev), torch.as_tensor(basis[uj]).to(dev)
+            if name == "c5":
+                sub = mops.gram_blocks4(kern._x_to_blocks(xs), kern._x_to_blocks(bs), mode=mops.GRAM_FULL)
+            else:
+                sub = mops.gram(mops.cov_basis(kern._x_to_sptm(xs), n), mops.cov_basis(kern._x_to_sptm(bs), n), 2.0 ** -n,
+                                mode=mops.GRAM_FULL)
+            exact = sub[torch.as_tensor(inv_i, device=dev), torch.as_tensor(inv_j, device=dev)].cpu().numpy()
+            last["exact_rel"] = parity_max_rel(exact, exact_ref, atol=0.0)
+            return max(rel, last["exact_rel"])
 
         def dominant():
             if name == "c5":
@@ -528,10 +621,13 @@ def build_workload(name: str, ctx: Ctx):
             kernel_name = "gram_blocks4_kernel"
         else:
             flops = gram_flops_per_entry(2 * n) * rect / ws
-            kernel_name = "gram_block_tiles_kernel<256,true>"
-        w.update(step=step, e2e_step=None, units=entries, e2e_units=0, metric="gram_entries_per_sec", unit="entries/s",
-                 scaling="strong", kernel=kernel_name, flops_per_launch=flops, launches_per_step=None, h2d=0, d2h=0,
-                 parity=parity, dominant=dominant, e2e_api=None)
+            kernel_name = "gram_panel_kernel"
+        w.update(step=step, e2e_step=e2e_step, units=entries, e2e_units=rect if e2e_step else 0,
+                 metric="gram_entries_per_sec", unit="entries/s", scaling="strong", kernel=kernel_name,
+                 flops_per_launch=flops, launches_per_step=None, h2d=(ns + nl) * nf * 8 if e2e_step else 0,
+                 d2h=ns * nl * 8 if e2e_step else 0, parity=parity, dominant=dominant,
+                 e2e_api="FermionicPQCKernel.__call__(x, landmarks) (pinned host features in, Gram copied to pinned "
+                         "host memory on rank 0)" if e2e_step else None)
     else:  # c4
         from matchcake_b200.operations import SptmCompRxRx, SptmCompRyRy, SptmCompRzRz
 
@@ -755,7 +851,8 @@ def main():
     time.sleep(0.1 if ctx.rank == 0 else 0.0)
 
     cpu_ok = ctx.rank == 0 and ctx.ws == 1 and not args.no_cpu_baseline
-    cpu_legs = {"c2": lambda: cpu_c2(65536, 10.0), "c3": lambda: cpu_c3(10.0)}
+    cpu_legs = {"c2": lambda: cpu_c2(65536, 10.0), "c3": lambda: cpu_c3(10.0), "c4": lambda: cpu_c4(10.0),
+                "c5": lambda: cpu_c5(10.0, 128), "c5c": lambda: cpu_c5(10.0, 256)}
     primary = build_workload(args.workload, ctx)
     rec = measure(primary, ctx, K, W, sampler, peaks, cpu_legs.get(args.workload) if cpu_ok else None,
                   sustained_s=0.0 if (args.no_sustained or args.workload != "c2") else 2.0)

@@ -21,6 +21,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra nvcc flags for experiments, e.g. MCB200_NVCC_EXTRA="-DMCB200_PANEL_PROFILE" python -m matchcake_b200.build --force
+NVCC_FLAGS += os.environ.get("MCB200_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):

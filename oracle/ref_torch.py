@@ -123,7 +123,14 @@ def projector_zero_lookup(r: torch.Tensor) -> torch.Tensor:
     obs = torch.zeros((r.shape[0], size, size), dtype=C)
     obs[:, iu[0], iu[1]] = vals.transpose(0, 1)
     obs = obs - torch.einsum("...ij->...ji", obs)
-    return torch.sqrt(torch.abs(torch.linalg.det(obs)) + 1e-32)
+    if size > 128:
+        # one matrix per LAPACK call: the batched complex LU of this torch/MKL build deadlocks for 256 x 256 matrices once
+        # torch.set_num_threads() has been called (nested threading); a loop is also what the reference's batch of
+        # one-pair circuits amounts to at this size
+        det = torch.stack([torch.linalg.det(o) for o in obs])
+    else:
+        det = torch.linalg.det(obs)
+    return torch.sqrt(torch.abs(det) + 1e-32)
 
 
 def readme_expvals(params: np.ndarray, n: int) -> np.ndarray:
