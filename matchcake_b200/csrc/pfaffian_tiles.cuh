@@ -32,7 +32,7 @@ struct Tiles {
 };
 
 __device__ __forceinline__ void dmma_acc(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
 }
