@@ -125,6 +125,16 @@ int mcb200_product_state_cov(const double* amplitudes_re_im, int64_t B, int32_t 
 int mcb200_cov_basis(const double* X, const int8_t* bits, int64_t B, int32_t n_qubits, int32_t m,
                      double* cov_out, void* stream);
 
+/* K1 + K2 in one call for basis-state inputs: cov[b] = (R_b^T Lambda_0(bits) R_b)[cols, cols] (m x m, full skew matrix)
+ * straight from the gate list -- mcb200_circuit_columns followed by mcb200_cov_basis without the (B, d, m) panel in
+ * global memory when the circuit is nearest-neighbour and the panel has at most 32 columns (marginals over <= 16 wires:
+ * qml.probs(wires), nif_device.py:430-479); other shapes run the two kernels through `workspace`
+ * (mcb200_circuit_cov_basis_workspace_bytes, 0 when fused). */
+int64_t mcb200_circuit_cov_basis_workspace_bytes(const mcb200_circuit_t* circuit_host, int64_t B, int32_t m);
+int mcb200_circuit_cov_basis(const mcb200_circuit_t* circuit_host, const double* params, int64_t B,
+                             const int32_t* cols, int32_t m, const int8_t* bits, double* cov_out,
+                             void* workspace, void* stream);
+
 /* General input: cov[b] = (R~^T L0 R~)[idx, idx] for a dense initial (extended) covariance L0 (D x D,
  * D = d or d+1; batch stride strideL0 = 0 if shared) and R (B, d, d) lifted by R (+) 1 when D = d+1
  * (devices/expval_strategies/m_pfaffian/_extended_covariance.py:101-126, nif_device.py:1134-1164).

@@ -48,6 +48,8 @@ SIGNATURES = {
     "mcb200_matchgate_sptm": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "mcb200_product_state_cov": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
     "mcb200_cov_basis": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp]),
+    "mcb200_circuit_cov_basis_workspace_bytes": (c_i64, [C.POINTER(CircuitStruct), c_i64, c_i32]),
+    "mcb200_circuit_cov_basis": (c_i32, [C.POINTER(CircuitStruct), c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "mcb200_cov_dense_workspace_bytes": (c_i64, [c_i64, c_i32, c_i32]),
     "mcb200_cov_dense": (c_i32, [c_vp, c_i64, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "mcb200_pfaffian_workspace_bytes": (c_i64, [c_i64, c_i32]),

@@ -6,6 +6,8 @@
 // Every gate is a 4x4 block on rows 2*wire0 .. 2*wire0+3, so one gate costs 8-16 FMA per column instead of
 // the 2 d^2 per column of the reference's dense padded product (devices/nif_device.py:195,
 // single_particle_transition_matrix.py:379-402).  Gates of one layer act on disjoint rows and run in parallel.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "circuit_dev.cuh"
 #include "pfaffian_dev.cuh"
@@ -305,6 +307,16 @@ extern "C" int mcb200_circuit_columns(const mcb200_circuit_t* circuit_host, cons
     const int rc = circuit_columns_brick_launch(c, params, B, cols, m, X_out, as_stream(stream));
     if (rc >= 0) return rc;
   }
+  // (the column-major panel kernel of circuit_panel.cu is used by mcb200_circuit_cov_basis only: for X itself it measures
+  // 1.60 ms against 1.37 ms of the row-major kernel below on config C4's pruned gate list, MCB200_PANEL_K1=1 selects it)
+  static const bool panel_k1 = [] {
+    const char* e = getenv("MCB200_PANEL_K1");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (panel_k1 && c.nearest_neighbour && m > 8 && m <= 32 && cols != nullptr) {
+    const int rc = circuit_panel_launch(c, params, B, cols, m, nullptr, X_out, nullptr, as_stream(stream));
+    if (rc >= 0) return rc;
+  }
   // coefficient buffer: at least one full layer (<= N gates on disjoint wires), normally 256 gates per batch
   const int max_layer_gates = c.n_qubits > 256 ? c.n_qubits : 256;
   // column chunk so that X (d x mc) + coefficients fit in shared memory
@@ -342,6 +354,38 @@ extern "C" int mcb200_cov_basis(const double* X, const int8_t* bits, int64_t B, 
     return rc;
   cov_basis_kernel<<<(unsigned)B, 256, smem, as_stream(stream)>>>(X, bits, n_qubits, m, cov_out);
   return check_launch("cov_basis_kernel");
+}
+
+// K1 + K2 in one call.  Fused (the column panel never leaves shared memory) for panels of up to 32 columns of
+// nearest-neighbour circuits; otherwise mcb200_circuit_columns into the workspace, then mcb200_cov_basis.
+static bool circuit_cov_fused(const CircuitDev& c, int m) {
+  return c.nearest_neighbour && c.n_gates > 0 && m >= 2 && m <= 32 && c.n_qubits <= 256 &&
+         (size_t)m * (2 * c.n_qubits + 2) * sizeof(double) <= 80 * 1024;
+}
+
+extern "C" int64_t mcb200_circuit_cov_basis_workspace_bytes(const mcb200_circuit_t* circuit_host, int64_t B, int32_t m) {
+  CircuitDev c;
+  if (circuit_to_dev(circuit_host, &c)) return -1;
+  if (B <= 0 || m <= 0 || circuit_cov_fused(c, m)) return 0;
+  return B * 2LL * c.n_qubits * m * (int64_t)sizeof(double);
+}
+
+extern "C" int mcb200_circuit_cov_basis(const mcb200_circuit_t* circuit_host, const double* params, int64_t B,
+                                        const int32_t* cols, int32_t m, const int8_t* bits, double* cov_out,
+                                        void* workspace, void* stream) {
+  CircuitDev c;
+  if (int rc = circuit_to_dev(circuit_host, &c)) return rc;
+  if (B < 0 || m < 0) return set_error("circuit_cov_basis: negative batch or column count");
+  if (B == 0 || m == 0) return 0;
+  if (cov_out == nullptr || cols == nullptr) return set_error("circuit_cov_basis: NULL pointer");
+  if (c.n_param_cols > 0 && params == nullptr) return set_error("circuit_cov_basis: params is NULL");
+  if (circuit_cov_fused(c, m)) {
+    const int rc = circuit_panel_launch(c, params, B, cols, m, bits, nullptr, cov_out, as_stream(stream));
+    if (rc >= 0) return rc;
+  }
+  if (workspace == nullptr) return set_error("circuit_cov_basis: this shape needs a workspace (see *_workspace_bytes)");
+  if (int rc = mcb200_circuit_columns(circuit_host, params, B, cols, m, (double*)workspace, stream)) return rc;
+  return mcb200_cov_basis((const double*)workspace, bits, B, c.n_qubits, m, cov_out, stream);
 }
 
 extern "C" int mcb200_circuit_expval_projector(const mcb200_circuit_t* circuit_host, const double* params,

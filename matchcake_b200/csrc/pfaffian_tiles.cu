@@ -1,6 +1,8 @@
 // K3 fast path for m <= 64: warp-per-matrix Pfaffians with the matrix held as DMMA accumulator fragments
 // (pfaffian_tiles.cuh).  Entry points are internal (declared in tiles_api.cuh) and are dispatched to from the
 // public C ABI in pfaffian.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "pfaffian_src.cuh"
 #include "pfaffian_tiles.cuh"
@@ -208,7 +210,9 @@ static int gram_tiles_launch(const double* cov0, const double* cov1, long long n
   };
   if constexpr (MT >= 8) {
     // 64 x 64: tile-row 0 of the working matrix in shared memory, one 12-warp block per SM at 168 registers.  Measured
-    // on C3 against (two tile-rows in shared memory, 2 x 8 warps at 128 registers): 278 ms vs 286 ms.
+    // on C3 (round 2, 4 x 4 block pivots): 249.5 ms against 281 ms (two tile-rows in shared memory, 16 warps at 128
+    // registers, spills), 270 ms (three tile-rows, 14 warps) and 259 ms (three tile-rows, 16 warps): more resident warps
+    // do not pay for the shared-memory traffic of the tiles they evict from the registers.
     return launch(gram_tiles_kernel<MT, 1, 3, 4, 1>, 3, 4, 1, GramSmem<MT, 1>::kPerWarp);
   } else {
     return launch(gram_tiles_kernel<MT, 0, 2, 8, 1>, 2, 8, 2, GramSmem<MT, 0>::kPerWarp);

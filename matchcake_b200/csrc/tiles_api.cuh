@@ -46,6 +46,10 @@ int cov_basis_gemm(const double* X, const int8_t* bits, long long B, int n_qubit
 struct CircuitDev;
 int circuit_columns_brick_launch(const CircuitDev& c, const double* params, long long B, const int32_t* cols, int m,
                                  double* X_out, cudaStream_t st);
+// K1 (+ K2) with a column-major shared-memory panel (circuit_panel.cu): nearest-neighbour circuits, narrow panels;
+// cov_out != NULL: write cov = X^T Lambda_0(bits) X (m x m) instead of X.  -1 = not applicable
+int circuit_panel_launch(const CircuitDev& c, const double* params, long long B, const int32_t* cols, int m,
+                         const int8_t* bits, double* X_out, double* cov_out, cudaStream_t st);
 // covariance route of the fused projector kernel (expval_cov.cu); -1 = tables do not fit shared memory
 int expval_cov_launch(const mcb200_circuit_t* h, const double* params, long long B, const int8_t* init_bits,
                       const int8_t* target_bits, double* out, cudaStream_t st);

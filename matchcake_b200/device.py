@@ -512,10 +512,10 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
     def _columns(self, maj: np.ndarray) -> torch.Tensor:
         """X = R[:, maj] (B, d, m) without forming R when the circuit is a single gate segment."""
         segments, _ = self._compile()
-        cols = torch.as_tensor(np.asarray(maj, dtype=np.int32), device=self.torch_device)
         if len(segments) == 1 and segments[0][0] == "gates" and self._sptm is None:
-            return _ops.circuit_columns(segments[0][1], segments[0][2], cols)
-        return self._materialize().index_select(2, cols.long()).contiguous()
+            return _ops.circuit_columns(segments[0][1], segments[0][2], np.asarray(maj))  # light cone cached per panel
+        cols = torch.as_tensor(np.asarray(maj, dtype=np.int64), device=self.torch_device)
+        return self._materialize().index_select(2, cols).contiguous()
 
     # ------------------------------------------------------------------ SPTM / covariance properties
     @property
@@ -555,9 +555,12 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
         if self._is_basis_input():
             if maj is None:
                 maj = np.arange(2 * n)
-            x = self._columns(maj)
-            bits = torch.as_tensor(sp.basis_state_bits().astype(np.int8), device=self.torch_device)
-            return _ops.cov_basis(x, n, bits)
+            bits = self._bits_device(sp.basis_state_bits())
+            segments, _ = self._compiled
+            if len(segments) == 1 and segments[0][0] == "gates" and self._sptm is None and len(maj) <= 32:
+                # marginal read-outs: gate list -> covariance block in one launch (light cone cached per panel)
+                return _ops.circuit_cov_basis(segments[0][1], segments[0][2], np.asarray(maj), bits)
+            return _ops.cov_basis(self._columns(maj), n, bits)
         l0 = _ops.product_state_cov(torch.as_tensor(sp.data[0], device=self.torch_device))
         idx = None if maj is None else torch.as_tensor(np.asarray(maj, dtype=np.int32), device=self.torch_device)
         return _ops.cov_dense(self._materialize(), l0, idx)
@@ -870,7 +873,7 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
         width = (1 << k) if target is None else 1
 
         def read_out(p_dev: torch.Tensor) -> torch.Tensor:
-            cov = _ops.cov_basis(_ops.circuit_columns(circ, p_dev, maj), n, bits)
+            cov = _ops.circuit_cov_basis(circ, p_dev, maj, bits)
             if target is None:
                 return _ops.probs_all(cov, normalize=True, floor2=floor2)
             return _ops.probs(cov, target, floor2=floor2)

@@ -115,6 +115,8 @@ class CompiledCircuit:
         self.gates_dev = torch.from_numpy(arr).to(self.device)
         self.layer_ptr_dev = torch.tensor(ptr, dtype=torch.int32, device=self.device)
         f = lambda a: None if a is None else torch.as_tensor(np.asarray(a, dtype=np.float64)).to(self.device)
+        self._host_arrays = (scale, bias, consts)      # kept for the light-cone sub-circuits
+        self._cones: dict = {}
         self.scale_dev, self.bias_dev, self.consts_dev = f(scale), f(bias), f(consts)
         if (self.scale_dev is None) != (self.bias_dev is None):
             raise ValueError("scale and bias must be given together")
@@ -129,6 +131,51 @@ class CompiledCircuit:
     @property
     def d(self) -> int:
         return 2 * self.n_qubits
+
+    # ------------------------------------------------------------------ backward light cone of a column panel
+    def light_cone_gates(self, cols: Sequence[int]) -> List[GateSpec]:
+        """Gates that can influence the columns ``cols`` of the SPTM.  X = G_0 (G_1 (... (G_{n-1} I[:, cols]))) is built
+        from the LAST gate backwards; a gate whose wires carry only structurally zero rows of the current panel acts on
+        zeros and is dropped (a long-range fSWAP touches every wire of its span).  Deep brickwork circuits measured on
+        a few wires lose a large part of their gates this way (config C4: 768 of 2016); the result is unchanged."""
+        support = np.zeros(self.n_qubits, dtype=bool)
+        support[np.asarray(list(cols), dtype=np.int64) // 2] = True
+        keep = []
+        for g in reversed(self.gates):
+            if support[g.wire0:g.wire1 + 1].any():
+                support[g.wire0:g.wire1 + 1] = True
+                keep.append(g)
+        keep.reverse()
+        return keep
+
+    def light_cone(self, cols) -> Tuple["CompiledCircuit", torch.Tensor]:
+        """(sub-circuit inside the light cone of ``cols``, ``cols`` as an int32 device tensor), cached per column set.
+        ``cols``: sequence / numpy array / tensor of Majorana indices.  The sub-circuit shares the parameter layout."""
+        if isinstance(cols, torch.Tensor):
+            key = ("t", cols.data_ptr(), cols.numel(), cols._version, str(cols.device))
+            hit = self._cones.get(key)
+            if hit is not None and hit[2]() is cols:
+                return hit[0], hit[1]
+            host = cols.detach().cpu().numpy().astype(np.int64).ravel()
+        else:
+            host = np.asarray(cols, dtype=np.int64).ravel()
+            key = ("h", host.tobytes())
+            hit = self._cones.get(key)
+            if hit is not None:
+                return hit[0], hit[1]
+        if host.size and (host.min() < 0 or host.max() >= self.d):
+            raise ValueError(f"column index out of range for {self.d} Majorana modes")
+        gates = self.light_cone_gates(host)
+        scale, bias, consts = self._host_arrays
+        sub = self if len(gates) == len(self.gates) else CompiledCircuit(
+            self.n_qubits, gates, self.n_param_cols, scale=scale, bias=bias, consts=consts, device=self.device)
+        cols_dev = torch.as_tensor(host.astype(np.int32), device=self.device)
+        if len(self._cones) > 32:
+            self._cones.clear()
+        import weakref
+
+        self._cones[key] = (sub, cols_dev, weakref.ref(cols) if isinstance(cols, torch.Tensor) else None)
+        return sub, cols_dev
 
     def _params(self, params: torch.Tensor) -> torch.Tensor:
         params = _f64(params, "params")
@@ -145,11 +192,34 @@ def _i8(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
     return None if t is None else t.to(device=device, dtype=torch.int8).contiguous()
 
 
-def circuit_columns(circ: CompiledCircuit, params: torch.Tensor, cols: Optional[torch.Tensor] = None) -> torch.Tensor:
+def circuit_columns(circ: CompiledCircuit, params: torch.Tensor, cols=None, prune: bool = True) -> torch.Tensor:
     """X[b] = R_b[:, cols] (B, d, m); ``cols=None`` gives the full SPTM (B, d, d).  Differentiable w.r.t. ``params``
-    (adjoint: mcb200_circuit_columns_backward un-applies the gates)."""
+    (adjoint: mcb200_circuit_columns_backward un-applies the gates).  ``cols`` may be a sequence, a numpy array or a
+    tensor; with ``prune`` only the gates inside the backward light cone of the panel are launched
+    (:meth:`CompiledCircuit.light_cone`, cached per column set) -- same result, fewer gates."""
     params = circ._params(params)
+    if cols is None:
+        return _op.circuit_columns(params, circ.handle, None)
+    if prune:
+        circ, cols = circ.light_cone(cols)
+    elif not isinstance(cols, torch.Tensor):
+        cols = torch.as_tensor(np.asarray(cols, dtype=np.int32))
     return _op.circuit_columns(params, circ.handle, _i32(cols, params.device))
+
+
+def circuit_cov_basis(circ: CompiledCircuit, params: torch.Tensor, cols, bits: Optional[torch.Tensor] = None,
+                      prune: bool = True) -> torch.Tensor:
+    """cov[b] = (R_b^T Lambda_0(bits) R_b)[cols, cols] (B, m, m) for a basis-state input: K1 + K2 in one launch when the
+    circuit is nearest-neighbour and the panel has at most 32 columns (the (B, d, m) panel stays in shared memory),
+    ``circuit_columns`` + ``cov_basis`` otherwise and whenever a parameter requires grad."""
+    if _ag.needs_grad(params):
+        return cov_basis(circuit_columns(circ, params, cols, prune=prune), circ.n_qubits, bits)
+    params = circ._params(params)
+    if prune:
+        circ, cols = circ.light_cone(cols)
+    elif not isinstance(cols, torch.Tensor):
+        cols = torch.as_tensor(np.asarray(cols, dtype=np.int32))
+    return _op.circuit_cov_basis(params, circ.handle, _i32(cols, params.device), _i8(bits, params.device))
 
 
 def circuit_expval_projector(circ: CompiledCircuit, params: torch.Tensor, init_bits: Optional[torch.Tensor] = None,

@@ -189,6 +189,26 @@ def _cc_backward(ctx, gx):
 _tl.register_autograd(f"{NS}::circuit_columns", _cc_backward, setup_context=_cc_setup)
 
 
+@_define("circuit_cov_basis", "(Tensor params, int circuit, Tensor cols, Tensor? bits) -> Tensor")
+def _circuit_cov_basis(params, circuit_handle, cols, bits):
+    """cov[b] = (R_b^T Lambda_0(bits) R_b)[cols, cols] straight from the gate list (K1 + K2 fused when the panel fits)."""
+    circ = circuit(circuit_handle)
+    params = _d(params, "params")
+    cols, ib = _i(cols, torch.int32, "cols"), _i(bits, torch.int8, "bits")
+    B, m = params.shape[0], cols.numel()
+    lib = _lib.load()
+    ws = _workspace(lib.mcb200_circuit_cov_basis_workspace_bytes(C.byref(circ._struct), B, m), params.device)
+    out = torch.empty((B, m, m), dtype=torch.float64, device=params.device)
+    check(lib.mcb200_circuit_cov_basis(C.byref(circ._struct), _p(params), B, _p(cols), m, _p(ib), _p(out), _p(ws),
+                                       _stream()))
+    return out
+
+
+@_fake("circuit_cov_basis")
+def _(params, circuit_handle, cols, bits):
+    return params.new_empty((params.shape[0], cols.numel(), cols.numel()), dtype=torch.float64)
+
+
 @_define("circuit_expval_projector",
          "(Tensor params, int circuit, Tensor? init_bits, Tensor? target_bits, float floor2) -> Tensor")
 def _circuit_expval_projector(params, circuit_handle, init_bits, target_bits, floor2):

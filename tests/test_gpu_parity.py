@@ -635,3 +635,107 @@ def test_pair_blocks_match_dense_covariance():
     for c in range(n // 2):
         off[:, 4 * c:4 * c + 4, 4 * c:4 * c + 4] = 0
     assert np.abs(off).max() < 1e-14  # the covariance really is block diagonal
+
+
+@pytest.mark.parametrize("n,depth,cols", [(12, 5, [0, 1, 6, 7]), (16, 20, [30, 31]), (10, 6, [4, 5, 18, 19]), (64, 64, list(range(16)))])
+def test_light_cone_pruning_keeps_the_columns(n, depth, cols):
+    """circuit_columns(prune=True) launches only the gates inside the backward light cone of the panel: same columns as
+    the full gate list (zeros may differ in sign), fewer gates; long-range fSWAPs and explicit blocks included."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(n + depth)
+    kinds = (mops.GATE_RXRX, mops.GATE_RYRY, mops.GATE_RZRZ)
+    g, off, consts = [], 0, []
+    for l in range(depth):
+        for q in range(l % 2, n - 1, 2):
+            g.append(mops.GateSpec(kinds[(l + q) % 3], q, q + 1, off))
+            off += 2
+        if l % 4 == 1 and n <= 16:
+            a, b = sorted(rng.choice(n, 2, replace=False))
+            g.append(mops.GateSpec(mops.GATE_FSWAP, int(a), int(b), 0, mops.FLAG_TRANSPOSE if l % 8 == 1 else 0))
+        if l % 5 == 2 and n <= 16:
+            q = int(rng.integers(0, n - 1))
+            g.append(mops.GateSpec(mops.GATE_BLOCK4_CONST, q, q + 1, len(consts)))
+            consts.extend(np.linalg.qr(rng.standard_normal((4, 4)))[0].reshape(-1).tolist())
+    circ = mops.CompiledCircuit(n, g, off, consts=np.asarray(consts) if consts else None)
+    params = dev(rng.uniform(0, 2 * np.pi, (5, off)))
+    sub, _ = circ.light_cone(cols)
+    assert len(sub.gates) <= len(circ.gates)
+    if depth < n // 2 or n == 64:
+        assert len(sub.gates) < len(circ.gates)   # shallow against the register / panel at the edge: gates really drop out
+    full = mops.circuit_columns(circ, params, cols, prune=False).cpu().numpy()
+    pruned = mops.circuit_columns(circ, params, np.asarray(cols)).cpu().numpy()
+    pruned_t = mops.circuit_columns(circ, params, torch.as_tensor(cols, device="cuda")).cpu().numpy()
+    # pruning drops exact zeros only; panels of 9..32 columns take the column-major kernel, whose fused multiply-adds may
+    # round differently from the row-major kernel's (1 ulp)
+    np.testing.assert_allclose(pruned, full, rtol=1e-12, atol=1e-15)
+    np.testing.assert_array_equal(pruned_t, pruned)
+    np.testing.assert_allclose(full, mops.circuit_columns(circ, params)[:, :, cols].cpu().numpy(), rtol=1e-12, atol=1e-15)
+    # gradients: the dropped gates get exact zeros
+    p = params.clone().requires_grad_(True)
+    w = dev(rng.standard_normal(full.shape))
+    (mops.circuit_columns(circ, p, cols) * w).sum().backward()
+    gp = p.grad.clone()
+    p.grad = None
+    (mops.circuit_columns(circ, p, cols, prune=False) * w).sum().backward()
+    np.testing.assert_allclose(gp.cpu().numpy(), p.grad.cpu().numpy(), rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("n,depth,cols,B", [(12, 9, [2, 3, 6, 7], 7), (16, 20, list(range(10, 22)), 5), (64, 64, list(range(16)), 9),
+                                            (40, 12, list(range(0, 32)), 3), (7, 5, [0, 1, 12, 13, 5], 4)])
+def test_fused_circuit_cov_basis_matches_two_kernels_and_oracle(n, depth, cols, B):
+    """mcb200_circuit_cov_basis (column-major panel kernel, covariance in the same block) == circuit_columns + cov_basis
+    (row-major kernels) == oracle; excited initial bits, adjacent fSWAPs and explicit blocks in the stream, odd panel
+    widths, the column kernel on its own (9..32 columns), and the unfused fall-back (long-range fSWAP)."""
+    from matchcake_b200 import ops as mops
+
+    rng = np.random.default_rng(n * depth)
+    kinds = (mops.GATE_RXRX, mops.GATE_RYRY, mops.GATE_RZRZ)
+    names = ("SptmCompRxRx", "SptmCompRyRy", "SptmCompRzRz")
+    g, oops, off, consts = [], [], 0, []
+    cols_p = []
+    for l in range(depth):
+        for q in range(l % 2, n - 1, 2):
+            k = (l + q) % 3
+            g.append(mops.GateSpec(kinds[k], q, q + 1, off))
+            cols_p.append((names[k], q, off))
+            off += 2
+        if l % 3 == 1:
+            q = int(rng.integers(0, n - 1))
+            g.append(mops.GateSpec(mops.GATE_FSWAP, q, q + 1, 0, mops.FLAG_TRANSPOSE if l % 2 else 0))
+            cols_p.append(("fswap", q, (q + 1, q) if l % 2 else (q, q + 1)))
+        if l % 4 == 2:
+            q = int(rng.integers(0, n - 1))
+            blk = np.linalg.qr(rng.standard_normal((4, 4)))[0]
+            g.append(mops.GateSpec(mops.GATE_BLOCK4_CONST, q, q + 1, len(consts)))
+            consts.extend(blk.reshape(-1).tolist())
+            cols_p.append(("block", q, blk))
+    params = rng.uniform(0, 2 * np.pi, (B, off))
+    for nm, q, o in cols_p:
+        if nm == "fswap":
+            oops.append(Op("SptmFSwap", o))
+        elif nm == "block":
+            oops.append(Op("Sptm", (q, q + 1), matrix=o))
+        else:
+            oops.append(Op(nm, (q, q + 1), params=params[:, o:o + 2]))
+    circ = mops.CompiledCircuit(n, g, off, consts=np.asarray(consts))
+    bits = rng.integers(0, 2, n)
+    p = dev(params)
+    fused = mops.circuit_cov_basis(circ, p, cols, torch.as_tensor(bits))
+    x = mops.circuit_columns(circ, p, cols)
+    two = mops.cov_basis(x, n, torch.as_tensor(bits))
+    np.testing.assert_allclose(fused.cpu().numpy(), two.cpu().numpy(), rtol=1e-13, atol=1e-14)
+    assert float((fused + fused.transpose(1, 2)).abs().max()) == 0.0
+    # the column-major kernel against the row-major one (same arithmetic, fused multiply-adds may round differently)
+    np.testing.assert_allclose(x.cpu().numpy(), mops.circuit_columns(circ, p)[:, :, cols].cpu().numpy(), rtol=1e-12, atol=1e-15)
+    r = gates.chain(oops, n)
+    amp = cv.amplitudes_from_basis_state(bits)
+    ref = cv.evolve(cv.covariance_matrix(amp), r)[:, cols][:, :, cols]
+    np.testing.assert_allclose(fused.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    # a long-range fSWAP switches the fused entry point to its two-kernel path (workspace)
+    if n <= 16:
+        g2 = g + [mops.GateSpec(mops.GATE_FSWAP, 0, n - 1, 0)]
+        circ2 = mops.CompiledCircuit(n, g2, off, consts=np.asarray(consts))
+        f2 = mops.circuit_cov_basis(circ2, p, cols, torch.as_tensor(bits))
+        t2 = mops.cov_basis(mops.circuit_columns(circ2, p, cols), n, torch.as_tensor(bits))
+        np.testing.assert_allclose(f2.cpu().numpy(), t2.cpu().numpy(), rtol=1e-13, atol=1e-15)

@@ -19,7 +19,7 @@ ENTRY_TO_OP = {
     "mcb200_cov_basis": "cov_basis", "mcb200_cov_dense": "cov_dense", "mcb200_pfaffian": "pfaffian",
     "mcb200_probs": "probs", "mcb200_probs_all": "probs_all", "mcb200_sector_features": "sector_features",
     "mcb200_rowdot": "rowdot", "mcb200_pauli_sum_small": "pauli_sum_small",
-    "mcb200_circuit_expval_projector": "circuit_expval_projector", "mcb200_gram": "gram_out",
+    "mcb200_circuit_expval_projector": "circuit_expval_projector", "mcb200_circuit_cov_basis": "circuit_cov_basis", "mcb200_gram": "gram_out",
     "mcb200_circuit_pair_blocks": "circuit_pair_blocks", "mcb200_gram_blocks4": "gram_blocks4_out",
     "mcb200_gram_symmetrize": "gram_symmetrize_", "mcb200_sample": "sample",
     "mcb200_pfaffian_backward": "pfaffian_backward", "mcb200_probs_backward": "probs_backward",
@@ -56,6 +56,7 @@ def test_fake_implementations_propagate_shapes_without_a_gpu():
     assert o.circuit_columns(p, circ.handle, _meta(3, dtype=torch.int32)).shape == (7, 8, 3)
     assert o.circuit_columns_backward(p, circ.handle, _meta(7, 8, 3), _meta(7, 8, 3)).shape == (7, 2)
     assert o.circuit_expval_projector(p, circ.handle, None, None, 0.0).shape == (7,)
+    assert o.circuit_cov_basis(p, circ.handle, _meta(4, dtype=torch.int32), None).shape == (7, 4, 4)
     assert o.circuit_pair_blocks(p, circ.handle, _meta(2, dtype=torch.int32), None).shape == (7, 2, 6)
     assert o.sptm_matmul(_meta(5, 6, 6), _meta(6, 6), False, True).shape == (5, 6, 6)
     a, b = o.matchgate_sptm(_meta(9, 4, 4, 2))
