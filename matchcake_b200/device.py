@@ -13,6 +13,7 @@ kernels (libmcb200), fused into a single launch for full-register projectors.  T
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict, defaultdict
 from typing import Any, Iterable, List, Optional, Sequence, Tuple, Union
 
@@ -38,6 +39,27 @@ PROBABILITY_STRATEGIES = {"lookuptable": "LookupTable", "productstate": "Product
 
 class DeviceError(Exception):
     """Unsupported operation / state preparation (stands in for ``pennylane.exceptions.DeviceError``)."""
+
+
+class _HostParams:
+    """Parameter matrix (B, P) of a gate segment that still lives in pinned host memory: the fused projector read-out
+    streams it in chunks (copy / compute overlap); every other consumer uploads it once through :meth:`device`."""
+
+    __slots__ = ("host", "_dev")
+
+    def __init__(self, host: torch.Tensor):
+        self.host = host
+        self._dev = None
+
+    def device(self, dev) -> torch.Tensor:
+        if self._dev is None:
+            self._dev = self.host.to(dev, non_blocking=True)
+        return self._dev
+
+
+def _seg_params(seg, dev) -> torch.Tensor:
+    p = seg[2]
+    return p.device(dev) if isinstance(p, _HostParams) else p
 
 
 def _is_projector(o) -> bool:
@@ -96,6 +118,11 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
     DEFAULT_CONTRACTION_METHOD = "neighbours"
     FUSED_MAX_QUBITS = 32  # 2N <= 64: warp-per-instance fused kernel; larger registers take K1 -> K2 -> K3 (block-tile Pfaffian)
     FUSED_SECTOR_MAX = 6   # Majorana strings up to this length take the fused Pauli-sum kernel
+    #: pinned host parameter matrices of at least this many bytes are streamed through the fused projector read-out in
+    #: STREAM_CHUNK_BYTES chunks (copy / compute overlap).  Config C2's 1 MB is far below: measured there, the stream and
+    #: event bookkeeping of 2 (4) chunks costs 0.06 (0.16) ms of host time against 0.03 ms of copies it could hide.
+    STREAM_MIN_BYTES = 64 << 20
+    STREAM_CHUNK_BYTES = 32 << 20
 
     @staticmethod
     def states_to_binary(samples: np.ndarray, num_wires: int, dtype: type = np.int64) -> np.ndarray:
@@ -147,6 +174,8 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
         self.torch_device = torch.device(kwargs.get("device", "cuda"))
         self.output_device = kwargs.get("output_device", "cpu")
         self.show_progress = kwargs.get("show_progress", False)
+        #: device -> host copies of large results go through pinned memory (the returned CPU tensor is page locked)
+        self.pinned_results = bool(kwargs.get("pinned_results", True))
         #: highest-probability basis state search (nif_device.py:241-246): "Greedy" / "FromSampling" or an instance
         self.star_state_finding_strategy = get_star_state_finding_strategy(
             kwargs.get("star_state_finding_strategy", "FromSampling"))
@@ -154,6 +183,7 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
         self._star_probability = None
         self.apply_metadata: defaultdict = defaultdict()
         self._bits_cache: dict = {}
+        self._wire_rows: dict = {}
         self._circuit_cache: "OrderedDict[tuple, _ops.CompiledCircuit]" = OrderedDict()
         self._group_cache: dict = {}
         self._plan_cache: "OrderedDict[tuple, tuple]" = OrderedDict()
@@ -243,7 +273,15 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
         if squeeze_batch and not self._batched:
             t = t.squeeze(-1) if t.ndim and t.shape[-1] == 1 else t
         t = t.to(self.R_DTYPE)
-        return t if self.output_device in (None, "cuda") else t.to(self.output_device)
+        if self.output_device in (None, "cuda"):
+            return t
+        if self.pinned_results and t.is_cuda and self.output_device == "cpu" and t.numel() >= 4096:
+            # large results: pinned staging + asynchronous copy + one stream synchronisation instead of a pageable copy
+            out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            out.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+            return out
+        return t.to(self.output_device)
 
     # ------------------------------------------------------------------ applying operations
     def apply_state_prep(self, operation, **kwargs) -> bool:
@@ -484,6 +522,12 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
         circ, sources = plan
         self._batched = batch is not None
         B = batch or 1
+        if len(sources) == 1:
+            t = prog[sources[0]]._given_params
+            if (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.dtype == torch.float64 and t.ndim == 2
+                    and t.numel() * 8 >= self.STREAM_MIN_BYTES and t.is_contiguous() and not t.requires_grad
+                    and t.is_pinned()):
+                return ([("gates", circ, _HostParams(t))], B)
         cols = []
         for j in sources:
             t = _as_f64_tensor(prog[j]._given_params, device=self.torch_device, keep_grad=True).reshape(-1, 2)
@@ -500,7 +544,7 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
         d = 2 * self.num_wires
         r = None
         for seg in segments:
-            rs = _ops.circuit_columns(seg[1], seg[2]) if seg[0] == "gates" else seg[1]
+            rs = _ops.circuit_columns(seg[1], _seg_params(seg, self.torch_device)) if seg[0] == "gates" else seg[1]
             r = rs if r is None else _ops.sptm_matmul(r, rs)
         if r is None:
             r = torch.eye(d, dtype=torch.float64, device=self.torch_device)[None]
@@ -513,7 +557,8 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
         """X = R[:, maj] (B, d, m) without forming R when the circuit is a single gate segment."""
         segments, _ = self._compile()
         if len(segments) == 1 and segments[0][0] == "gates" and self._sptm is None:
-            return _ops.circuit_columns(segments[0][1], segments[0][2], np.asarray(maj))  # light cone cached per panel
+            return _ops.circuit_columns(segments[0][1], _seg_params(segments[0], self.torch_device),
+                                        np.asarray(maj))  # light cone cached per panel
         cols = torch.as_tensor(np.asarray(maj, dtype=np.int64), device=self.torch_device)
         return self._materialize().index_select(2, cols).contiguous()
 
@@ -559,7 +604,8 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
             segments, _ = self._compiled
             if len(segments) == 1 and segments[0][0] == "gates" and self._sptm is None and len(maj) <= 32:
                 # marginal read-outs: gate list -> covariance block in one launch (light cone cached per panel)
-                return _ops.circuit_cov_basis(segments[0][1], segments[0][2], np.asarray(maj), bits)
+                return _ops.circuit_cov_basis(segments[0][1], _seg_params(segments[0], self.torch_device), np.asarray(maj),
+                                              bits)
             return _ops.cov_basis(self._columns(maj), n, bits)
         l0 = _ops.product_state_cov(torch.as_tensor(sp.data[0], device=self.torch_device))
         idx = None if maj is None else torch.as_tensor(np.asarray(maj, dtype=np.int32), device=self.torch_device)
@@ -578,7 +624,7 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
         if not torch.is_grad_enabled():
             return False
         segments, _ = self._compile()
-        return any(isinstance(t, torch.Tensor) and t.requires_grad for seg in segments for t in seg[1:])
+        return any(isinstance(t, torch.Tensor) and t.requires_grad for seg in segments for t in seg[1:])  # _HostParams: no grad
 
     def _ext_cov_device(self) -> torch.Tensor:
         if self._grad_mode() and self._is_basis_input():
@@ -631,11 +677,43 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
                 and segments[0][0] == "gates" and n <= self.FUSED_MAX_QUBITS):
             bits = self._bits_device(self._state_prep_op.basis_state_bits())
             tgt = self._bits_device(target[0])
-            return _ops.circuit_expval_projector(segments[0][1], segments[0][2], bits, tgt, floor2=floor2)[:, None]
+            p = segments[0][2]
+            if isinstance(p, _HostParams) and self.output_device == "cpu" and p._dev is None:
+                return self._projector_streamed(segments[0][1], p.host, bits, tgt, floor2)[:, None]
+            return _ops.circuit_expval_projector(segments[0][1], _seg_params(segments[0], self.torch_device), bits, tgt,
+                                                 floor2=floor2)[:, None]
         maj = np.stack([2 * wire_idx, 2 * wire_idx + 1], axis=1).ravel()
         cov = self._cov_device(maj)
         outcomes = torch.as_tensor(np.ascontiguousarray(target.astype(np.int8)), device=self.torch_device)
         return _ops.probs(cov, outcomes, floor2=floor2)
+
+    def _projector_streamed(self, circ, host_params: torch.Tensor, bits, tgt, floor2: float) -> torch.Tensor:
+        """Fused projector read-out of pinned host parameters in STREAM_CHUNK_BYTES chunks: the H2D copy of chunk c+1 runs on a
+        copy stream under the kernel of chunk c, each chunk's values return on a third stream into one pinned host
+        vector, which is what the caller gets (no separate device -> host pass)."""
+        dev = self.torch_device
+        B = host_params.shape[0]
+        rows = max(1, min(B, self.STREAM_CHUNK_BYTES // max(1, host_params.shape[1] * 8)))
+        main = torch.cuda.current_stream(dev)
+        copy_in, copy_out = self._side_streams()
+        out = torch.empty((B,), dtype=torch.float64, pin_memory=True)
+        copy_in.wait_stream(main)
+        copy_out.wait_stream(main)
+        for s0 in range(0, B, rows):
+            e0 = min(B, s0 + rows)
+            with torch.cuda.stream(copy_in):
+                buf = host_params[s0:e0].to(dev, non_blocking=True)
+                ready = copy_in.record_event()
+            main.wait_event(ready)
+            buf.record_stream(main)
+            res = _ops.circuit_expval_projector(circ, buf, bits, tgt, floor2=floor2)
+            done = main.record_event()
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(done)
+                out[s0:e0].copy_(res, non_blocking=True)
+                res.record_stream(copy_out)
+        copy_out.synchronize()
+        return out
 
     def get_states_probability(self, target_binary_states, wires=None, **kwargs):
         """Scalar / (B,) for one outcome ``(k,)``; ``(Bq,)`` / ``(Bq, B)`` for a batch ``(Bq, k)`` (:742-810)."""
@@ -651,13 +729,33 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
         is_single = target.ndim == 1
         if wires is None:
             wires = self.wires
-        w = np.asarray(_wires_tuple(wires) if not isinstance(wires, np.ndarray) else wires, dtype=object)
-        if is_single:
-            assert len(target) == w.shape[-1], (
-                f"The target binary state must have {w.shape[-1]} elements. Got {len(target)} instead.")
-            target = target[None]
-        if w.ndim == 1:
-            # one shared wire list: map it once (the common case of a single projector / qml.probs)
+        row = None
+        if not isinstance(wires, np.ndarray):
+            # one shared wire list (a single projector / qml.probs): the label -> index map is cached per wire tuple
+            wt = _wires_tuple(wires)
+            if not (len(wt) and isinstance(wt[0], (list, tuple, np.ndarray))):
+                row = self._wire_rows.get(wt)
+                if row is None:
+                    if len(self._wire_rows) > 64:
+                        self._wire_rows.clear()
+                    row = self._wire_rows[wt] = np.fromiter((self._wire_index(x) for x in wt), dtype=int, count=len(wt))
+        if row is not None:
+            if is_single:
+                assert len(target) == len(row), (
+                    f"The target binary state must have {len(row)} elements. Got {len(target)} instead.")
+                target = target[None]
+            widx = row[None]
+            same = True
+            w = None
+        else:
+            w = np.asarray(wires, dtype=object)
+            if is_single:
+                assert len(target) == w.shape[-1], (
+                    f"The target binary state must have {w.shape[-1]} elements. Got {len(target)} instead.")
+                target = target[None]
+        if row is not None:
+            pass
+        elif w.ndim == 1:
             row = np.fromiter((self._wire_index(x) for x in w), dtype=int, count=len(w))
             widx = np.broadcast_to(row, target.shape)
             same = True

@@ -23,6 +23,11 @@ TensorLike = Union[np.ndarray, torch.Tensor, Sequence[float]]
 
 
 def _wires_tuple(wires) -> Tuple[Any, ...]:
+    t = type(wires)
+    if t is tuple:
+        return wires
+    if t is list:
+        return tuple(wires)
     if wires is None:
         return ()
     if isinstance(wires, (int, np.integer, str)):
@@ -180,12 +185,12 @@ class CompRotation(MatchgateOperation):
     GATE_KIND = _ops.GATE_RXRX
 
     def __init__(self, params: TensorLike, wires=None, **kwargs):
-        Operation.__init__(self, wires)
-        if len(self.wires) != 2 or self.wires[1] - self.wires[0] != 1:
+        w = self.wires = _wires_tuple(wires)
+        if len(w) != 2 or w[1] - w[0] != 1:
             raise AssertionError(f"{self.name} requires 2 consecutive wires, got {self.wires}.")
-        shp = _shape(params)
+        shp = params.shape if hasattr(params, "shape") else np.shape(params)
         if len(shp) not in (1, 2) or shp[-1] != 2:
-            raise ValueError(f"Invalid shape for the parameters: {shp}. Expected (2,) or (batch, 2).")
+            raise ValueError(f"Invalid shape for the parameters: {tuple(shp)}. Expected (2,) or (batch, 2).")
         self._given_params = params
         self.kwargs = kwargs
 
@@ -259,8 +264,8 @@ class CompZX(MatchgateOperation):
     """fSWAP = M(Z, X) (fermionic_swap.py:15-61)."""
 
     def __init__(self, wires=None, **kwargs):
-        Operation.__init__(self, wires)
-        if len(self.wires) != 2 or abs(self.wires[1] - self.wires[0]) != 1:
+        w = self.wires = _wires_tuple(wires)
+        if len(w) != 2 or abs(w[1] - w[0]) != 1:
             raise AssertionError(f"fSWAP as a matchgate requires 2 consecutive wires, got {self.wires}.")
         self.kwargs = kwargs
 

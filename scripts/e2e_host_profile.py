@@ -7,7 +7,8 @@ from matchcake_b200.observables import Projector
 n, B = 16, 65536
 rng = np.random.default_rng(0)
 host = [torch.as_tensor(rng.uniform(0, 2 * np.pi, (B, 2))).pin_memory() for _ in range(4)]
-qdev = mc.NonInteractingFermionicDevice(wires=n, output_device="cpu")
+import os
+qdev = mc.NonInteractingFermionicDevice(wires=n, output_device="cpu", pinned_results=os.environ.get("PINNED", "1") == "1")
 def circuit_ops(p):
     for w in range(0, n - 1, 2):
         yield CompRxRx(p, wires=[w, w + 1]); yield CompRyRy(p, wires=[w, w + 1]); yield CompRzRz(p, wires=[w, w + 1])

@@ -420,3 +420,29 @@ def test_execute_layered_equals_the_op_stream(host):
         dev.execute_layered(layout, p_in)
     with pytest.raises(mc.DeviceError):
         dev.execute_layered([(MatchgateOperation, 0)], p_in, probs_wires=[0])
+
+
+@pytest.mark.gpu
+def test_streamed_host_parameters_equal_device_resident_ones():
+    """Pinned host parameters of a large batch go through the fused projector kernel in chunks (copy / compute overlap):
+    same values as the device-resident batch, bit for bit; later read-outs of the same program still work."""
+    n, B = 8, 20001   # odd batch: ragged last chunk
+    rng = np.random.default_rng(3)
+    p = rng.uniform(0, 2 * np.pi, (B, 2))
+    proj = obs.Projector(np.zeros(n, dtype=int), wires=range(n))
+    dev_s = mc.NIFDevice(n)
+    dev_s.STREAM_MIN_BYTES, dev_s.STREAM_CHUNK_BYTES = 1 << 16, 96 * 1024   # force the streamed path: 4 chunks of 6144 rows
+    host = torch.as_tensor(p).pin_memory()
+    got = dev_s.execute_generator(_readme_stream(host, n), observable=proj, output_type="expval", reset=True)
+    dev_d = mc.NIFDevice(n)
+    ref = dev_d.execute_generator(_readme_stream(torch.as_tensor(p).cuda(), n), observable=proj, output_type="expval",
+                                  reset=True)
+    assert got.device.type == "cpu" and got.shape == (B,)
+    np.testing.assert_array_equal(got.numpy(), ref.numpy())
+    sel = rng.choice(B, 64, replace=False)
+    zeros = np.zeros(n, dtype=int)
+    np.testing.assert_allclose(got.numpy()[sel], readout.probs_lookup_table(_readme_oracle(p[sel], n), zeros, zeros, np.arange(n)),
+                               rtol=RTOL, atol=ATOL)
+    # the same (still host-resident) program serves other read-outs
+    pr = dev_s.analytic_probability([0, 1])
+    np.testing.assert_array_equal(pr.numpy(), dev_d.analytic_probability([0, 1]).numpy())
