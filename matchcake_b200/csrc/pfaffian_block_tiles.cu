@@ -72,6 +72,16 @@ static bool use_slab_variant() {
   return v;
 }
 
+// 64 < m <= 128: the pass kernels of pfaffian_panel.cu (5.8 against 4.3 M Pfaffians/s at m = 128, 9.0 against 8.1 at m = 96,
+// threshold pivoting in place) unless MCB200_PF128_OLD=1 asks for the round-1 kernels of this file (A/B measurements)
+static bool use_static128() {
+  static const bool v = [] {
+    const char* e = getenv("MCB200_PF128_OLD");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return v;
+}
+
 long long block_tiles_workspace_bytes(long long n_items, int m) {
   if (m <= 128) return 0;
   if (!use_slab_variant()) return panel_workspace_bytes(n_items, m);
@@ -111,6 +121,7 @@ int block_tiles_gram(const double* cov0, const double* cov1, long long n0, long 
   const int MT = (d + 7) / 8, NT = MT * (MT + 1) / 2;
   if (d > 128 && !use_slab_variant())
     return panel_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, workspace, st);
+  if (d <= 128 && use_static128()) return static128_gram(cov0, cov1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, st);
   GramBtArgs g{cov0, cov1, n0, n1, d, row_begin, rows, mode, scale, K, ldk, g_abs_floor2};
   const long long cells = rows * n1;
   if (d <= 128) {
@@ -133,18 +144,21 @@ int block_tiles_gram(const double* cov0, const double* cov1, long long n0, long 
 int block_tiles_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out, void* workspace,
                                cudaStream_t st) {
   if (m > 128 && !use_slab_variant()) return panel_pfaffian_plain(A, n, m, mode, scale, out, workspace, st);
+  if (m <= 128 && use_static128()) return static128_pfaffian_plain(A, n, m, mode, scale, out, st);
   PlainSrc s{A, m};
   return launch_block_tiles(s, n, m, mode, scale, out, workspace, st, "pfaffian_block_tiles_kernel");
 }
 
 int block_tiles_pfaffian_probs(const double* cov, const int8_t* outcomes, long long B, int Q, int k, double* out,
                                cudaStream_t st) {
+  if (use_static128()) return static128_pfaffian_probs(cov, outcomes, B, Q, k, out, st);
   ProbsSrc s{cov, outcomes, Q, k, 2 * k};
   return launch_block_tiles(s, B * Q, 2 * k, MCB200_PF_ABS, ldexp(1.0, -k), out, nullptr, st, "probs_block_tiles_kernel");
 }
 
 int block_tiles_pfaffian_sector(const double* cov, long long B, int D, const int32_t* index_sets, int T, int s,
                                 double* feats, cudaStream_t st) {
+  if (use_static128()) return static128_pfaffian_sector(cov, B, D, index_sets, T, s, feats, st);
   SectorSrc src{cov, index_sets, D, T, s};
   return launch_block_tiles(src, B * T, s, MCB200_PF_SIGNED, 1.0, feats, nullptr, st, "sector_block_tiles_kernel");
 }

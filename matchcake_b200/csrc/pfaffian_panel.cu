@@ -226,7 +226,9 @@ __device__ __forceinline__ void panel_argmax(const double* vec, int R1, int hi, 
 // acceptable pivot below `stop`); pf is multiplied by the signed pivots.
 // TWO: records 1 / pivot per pair in pinv and keeps the A12 part of every eliminated row as it was when its pair was
 // eliminated (rows R+2, R+3 exist only as vectors once the first pair has been applied to them: they are written back).
-template <bool TWO>
+// NC = column capacity (256: blocks of 512 threads; 128: blocks of 256 threads): threads [0, NC) own one column each,
+// threads [NC, 2 NC) extract the second pair's rows.
+template <bool TWO, int NC = 256>
 __device__ int panel_static(double2* tiles, const PanelLayout<TWO>& L, const PanelTri& tri, int m, int stop, double* vec,
                             double* pinv, unsigned* kmx, double& pf) {
   const int tid = threadIdx.x, lane = tid & 31, gr = lane >> 2, tg = lane & 3;
@@ -245,8 +247,8 @@ __device__ int panel_static(double2* tiles, const PanelLayout<TWO>& L, const Pan
     const bool has2 = R + 3 < stop;  // a second pair exists inside [0, stop)
     {
       // rows R .. R+3 -> vectors; kmx[k] = largest |entry| of row R+k right of the pair (high word), for the guards
-      const int c = tid & 255;
-      if (tid < 256) {
+      const int c = tid & (NC - 1);
+      if (tid < NC) {
         const PanelRow<TWO> r0(tiles, L, R), r1(tiles, L, R + 1);
         const double x = (c > R && c < m) ? r0.at(c) : 0.0, y = (c > R + 1 && c < m) ? r1.at(c) : 0.0;
         u[c] = x;
@@ -257,7 +259,7 @@ __device__ int panel_static(double2* tiles, const PanelLayout<TWO>& L, const Pan
           if (kx) atomicMax(&kmx[0], kx);
           if (ky) atomicMax(&kmx[1], ky);
         }
-      } else if (tid < 512 && has2) {
+      } else if (tid < 2 * NC && has2) {
         const PanelRow<TWO> r2(tiles, L, R + 2), r3(tiles, L, R + 3);
         const double x = (c > R + 2 && c < m) ? r2.at(c) : 0.0;
         u2[c] = x;
@@ -288,14 +290,14 @@ __device__ int panel_static(double2* tiles, const PanelLayout<TWO>& L, const Pan
         }
         __syncthreads();
         {
-          const int c = tid & 255;
-          if (tid < 256) {
+          const int c = tid & (NC - 1);
+          if (tid < NC) {
             const PanelRow<TWO> r1(tiles, L, R + 1);
             const double y = (c > R + 1 && c < m) ? r1.at(c) : 0.0;
             v[c] = y;
             const unsigned ky = __reduce_max_sync(0xffffffffu, c > R + 3 ? ((unsigned)__double2hiint(y) & 0x7fffffffu) : 0u);
             if (lane == 0 && ky) atomicMax(&kmx[1], ky);
-          } else if (tid < 512 && has2) {
+          } else if (tid < 2 * NC && has2) {
             const PanelRow<TWO> r2(tiles, L, R + 2), r3(tiles, L, R + 3);
             const double x = (c > R + 2 && c < m) ? r2.at(c) : 0.0;
             u2[c] = x;
@@ -332,7 +334,7 @@ __device__ int panel_static(double2* tiles, const PanelLayout<TWO>& L, const Pan
     }
     pf *= quad ? piv1 * piv2 : piv1;
     const int dead = quad ? R + 3 : R + 1;  // indices <= dead leave the matrix with this pass
-    if (tid < 256) {
+    if (tid < NC) {
       const int c = tid;
       const bool live = c > dead;
       const double uc = u[c], wc = v[c];
@@ -535,6 +537,126 @@ __global__ void __launch_bounds__(kPanelThreads) gram_panel_kernel(GramBtArgs g,
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 64 < m <= 128: the same pass structure on the whole matrix (no panel split): 136 tiles in shared memory, blocks of 256
+// threads, two blocks per SM; threshold pivoting in place, the pivoted tail of pfaffian_block_tiles.cuh only for rows that
+// have no acceptable pivot at all.
+constexpr int kStatic128Threads = 256;
+
+template <class Src>
+__device__ double static128_pfaffian(const Src& src, long long item, int m, double2* tiles, double* vec, unsigned* kmx,
+                                     const PanelTri& tri) {
+  const int MT = (m + 7) >> 3;
+  const int lane = lane_id(), w = warp_id(), gr = lane >> 2, tg = lane & 3, nw = (int)(blockDim.x >> 5);
+  if (threadIdx.x == 0) kmx[0] = kmx[1] = kmx[2] = 0u;
+  for (int ti = w; ti < MT; ti += nw) {
+#pragma unroll 4
+    for (int tj = ti; tj < MT; ++tj)
+      tiles[bt_idx(MT, ti, tj) * 32 + lane] = make_double2(src.at(item, 8 * ti + gr, 8 * tj + 2 * tg),
+                                                           src.at(item, 8 * ti + gr, 8 * tj + 2 * tg + 1));
+  }
+  __syncthreads();
+  double pf = 1.0;
+  const PanelLayout<false> L{MT, MT};
+  const int done = panel_static<false, 128>(tiles, L, tri, m, m, vec, nullptr, kmx, pf);
+  if (done < m) {
+    __syncthreads();
+    return bt_pivoted_tail<128>(tiles, MT, m, done, vec, pf);
+  }
+  return pf;
+}
+
+__host__ __device__ constexpr size_t static128_smem_bytes(int m) {
+  return (size_t)(((m + 7) >> 3) * (((m + 7) >> 3) + 1) / 2) * 32 * sizeof(double2) +
+         (size_t)(8 * kPanelVS + 2 + 8) * sizeof(double);
+}
+
+template <class Src>
+__global__ void __launch_bounds__(kStatic128Threads, 2) pfaffian_static128_kernel(Src src, long long n_items, int m,
+                                                                                 int out_mode, double scale,
+                                                                                 double floor2, double* out) {
+  extern __shared__ __align__(16) unsigned char pn_smem[];
+  const int MT = (m + 7) >> 3, NT = MT * (MT + 1) / 2;
+  double2* tiles = reinterpret_cast<double2*>(pn_smem);
+  double* vec = reinterpret_cast<double*>(tiles + NT * 32);
+  unsigned* kmx = reinterpret_cast<unsigned*>(vec + 8 * kPanelVS);
+  PanelTri* tri = reinterpret_cast<PanelTri*>(vec + 8 * kPanelVS + 2);
+  if (threadIdx.x == 0) panel_build_tri(tri, MT);
+  __syncthreads();
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const double pf = static128_pfaffian(src, item, m, tiles, vec, kmx, *tri);
+    if (threadIdx.x == 0) out[item] = out_mode == MCB200_PF_SIGNED ? scale * pf : abs_floor(scale * pf, floor2);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kStatic128Threads, 2) gram_static128_kernel(GramBtArgs g) {
+  extern __shared__ __align__(16) unsigned char pn_smem[];
+  const int m = g.d, MT = (m + 7) >> 3, NT = MT * (MT + 1) / 2;
+  double2* tiles = reinterpret_cast<double2*>(pn_smem);
+  double* vec = reinterpret_cast<double*>(tiles + NT * 32);
+  unsigned* kmx = reinterpret_cast<unsigned*>(vec + 8 * kPanelVS);
+  PanelTri* tri = reinterpret_cast<PanelTri*>(vec + 8 * kPanelVS + 2);
+  if (threadIdx.x == 0) panel_build_tri(tri, MT);
+  __syncthreads();
+  const bool upper = g.n0 < g.n1;
+  for (long long cell = blockIdx.x; cell < g.rows * g.n1; cell += gridDim.x) {
+    const long long i = g.row_begin + cell / g.n1, j = cell % g.n1;
+    if (g.mode != MCB200_GRAM_FULL && !(upper ? (j > i) : (i > j))) continue;
+    GramPairSrc src{g.cov0 + i * (long long)m * m, g.cov1 + j * (long long)m * m, m};
+    const double pf = static128_pfaffian(src, 0, m, tiles, vec, kmx, *tri);
+    if (threadIdx.x == 0) {
+      const double val = abs_floor(g.scale * pf, g.floor2);
+      g.K[i * g.ldk + j] = val;
+      if (g.mode == MCB200_GRAM_REFERENCE && j < g.n0 && i < g.n1) g.K[j * g.ldk + i] = val;  // gram_matrix.py:139-143
+    }
+    __syncthreads();
+  }
+}
+
+template <class Src>
+static int static128_launch(const Src& src, long long n_items, int m, int out_mode, double scale, double* out,
+                            cudaStream_t st, const char* what) {
+  if (n_items == 0) return 0;
+  const size_t smem = static128_smem_bytes(m);
+  auto kernel = pfaffian_static128_kernel<Src>;
+  if (int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), what)) return rc;
+  const long long per_sm = (long long)(kMaxDynSmem / (smem + 1024)) < 4 ? (long long)(kMaxDynSmem / (smem + 1024)) : 4;
+  const long long cap = per_sm * kNumSMs;
+  kernel<<<(unsigned)(n_items < cap ? n_items : cap), kStatic128Threads, smem, st>>>(src, n_items, m, out_mode, scale,
+                                                                                    g_abs_floor2, out);
+  return check_launch(what);
+}
+
+int static128_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out, cudaStream_t st) {
+  PlainSrc s{A, m};
+  return static128_launch(s, n, m, mode, scale, out, st, "pfaffian_static128_kernel");
+}
+int static128_pfaffian_probs(const double* cov, const int8_t* outcomes, long long B, int Q, int k, double* out,
+                             cudaStream_t st) {
+  ProbsSrc s{cov, outcomes, Q, k, 2 * k};
+  return static128_launch(s, B * Q, 2 * k, MCB200_PF_ABS, ldexp(1.0, -k), out, st, "probs_static128_kernel");
+}
+int static128_pfaffian_sector(const double* cov, long long B, int D, const int32_t* index_sets, int T, int sz,
+                              double* feats, cudaStream_t st) {
+  SectorSrc s{cov, index_sets, D, T, sz};
+  return static128_launch(s, B * T, sz, MCB200_PF_SIGNED, 1.0, feats, st, "sector_static128_kernel");
+}
+int static128_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
+                   long long row_end, int mode, double scale, double* K, long long ldk, cudaStream_t st) {
+  const long long rows = row_end - row_begin;
+  if (rows <= 0 || n1 <= 0) return 0;
+  GramBtArgs g{cov0, cov1, n0, n1, d, row_begin, rows, mode, scale, K, ldk, g_abs_floor2};
+  const size_t smem = static128_smem_bytes(d);
+  if (int rc = check_cuda(cudaFuncSetAttribute(gram_static128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)smem), "cudaFuncSetAttribute(gram_static128)"))
+    return rc;
+  const long long per_sm = (long long)(kMaxDynSmem / (smem + 1024)) < 4 ? (long long)(kMaxDynSmem / (smem + 1024)) : 4;
+  const long long cells = rows * n1, cap = per_sm * kNumSMs;
+  gram_static128_kernel<<<(unsigned)(cells < cap ? cells : cap), kStatic128Threads, smem, st>>>(g);
+  return check_launch("gram_static128_kernel");
 }
 
 // one block per SM (200 KB of shared memory); the slabs are only touched by the fallback

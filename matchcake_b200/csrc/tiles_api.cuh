@@ -33,6 +33,14 @@ int panel_pfaffian_plain(const double* A, long long n, int m, int mode, double s
                          cudaStream_t st);
 int panel_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
                long long row_end, int mode, double scale, double* K, long long ldk, void* workspace, cudaStream_t st);
+// 64 < m <= 128 with the pass structure of the panel kernel (threshold pivoting in place, 256-thread blocks)
+int static128_pfaffian_plain(const double* A, long long n, int m, int mode, double scale, double* out, cudaStream_t st);
+int static128_pfaffian_probs(const double* cov, const int8_t* outcomes, long long B, int Q, int k, double* out,
+                             cudaStream_t st);
+int static128_pfaffian_sector(const double* cov, long long B, int D, const int32_t* index_sets, int T, int s,
+                              double* feats, cudaStream_t st);
+int static128_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
+                   long long row_end, int mode, double scale, double* K, long long ldk, cudaStream_t st);
 long long tiles_gram_workspace_bytes(long long n0, long long n1, int d);
 int tiles_gram(const double* cov0, const double* cov1, long long n0, long long n1, int d, long long row_begin,
                long long row_end, int mode, double scale, double* K, long long ldk, void* workspace,
