@@ -1,4 +1,4 @@
-"""Small single-GPU targets for ncu: python scripts/profile_target.py {c2|gram|c4|blocks|matmul|pf} [size]"""
+"""Small single-GPU targets for ncu: python scripts/profile_target.py {c2|gram|c4|c4cols|blocks|matmul|pf|pfcov} [size]"""
 import sys
 
 import numpy as np
@@ -38,8 +38,18 @@ elif what == "c4":
     params = torch.rand((B, off), dtype=torch.float64, device=dev) * (2 * np.pi)
     maj = torch.arange(2 * k, dtype=torch.int32, device=dev)
     for _ in range(2):
-        x = mops.circuit_columns(circ, params, maj)
-        out = mops.probs_all(mops.cov_basis(x, n), normalize=True)
+        out = mops.probs_all(mops.circuit_cov_basis(circ, params, maj), normalize=True)   # fused K1 + K2, then the tree
+elif what == "c4cols":  # K1 alone on C4's 16-column panel (row-major kernel, light-cone pruned gate list)
+    n, B, depth, k = 64, size or 4096, 64, 8
+    gates = []; off = 0
+    kinds = (mops.GATE_RXRX, mops.GATE_RYRY, mops.GATE_RZRZ)
+    for l in range(depth):
+        for w in range(l % 2, n - 1, 2):
+            gates.append(mops.GateSpec(kinds[l % 3], w, w + 1, off)); off += 2
+    circ = mops.CompiledCircuit(n, gates, off)
+    params = torch.rand((B, off), dtype=torch.float64, device=dev) * (2 * np.pi)
+    for _ in range(2):
+        out = mops.circuit_columns(circ, params, np.arange(2 * k))
 elif what == "blocks":
     n = size or 32768
     b0 = torch.randn(n, 64, 6, dtype=torch.float64, device=dev)
