@@ -76,6 +76,14 @@ int mcb200_version(void);
 const char* mcb200_last_error(void);
 int mcb200_device_count(void);
 
+/* Host-side check of a circuit descriptor (synchronous: the gate list and the layer table are copied to the host).
+ * The compute entry points TRUST the descriptor: every layer holds gates on disjoint wires (hence at most N/2 gates, which
+ * is what the kernels' shared-memory coefficient buffers are sized for), wires are in range, two-qubit blocks act on
+ * consecutive wires, parameter columns lie inside the parameter row, nearest_neighbour is only set when it is true.  A
+ * host that builds descriptors itself calls this once per circuit structure (matchcake_b200.ops.CompiledCircuit
+ * enforces the same rules when it builds one). */
+int mcb200_circuit_validate(const mcb200_circuit_t* circuit_host);
+
 /* Magnitude floor, sticky per calling thread.  The reference's probability read-outs are
  * utils.pfaffian(sign=False) = torch_pfaffian.PfaffianDet = sqrt(|det A| + EPSILON), EPSILON = 1e-32
  * (utils/_pfaffian.py:81,110-118; a process-wide global the reference mutates under a lock before every call).

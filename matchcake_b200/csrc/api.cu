@@ -1,6 +1,9 @@
 // Library plumbing: error reporting, launch accounting and FP64 peak probes.
 #include <stdarg.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "tiles_api.cuh"
 
@@ -84,6 +87,53 @@ extern "C" int mcb200_set_abs_floor(double floor2) {
   return 0;
 }
 extern "C" double mcb200_get_abs_floor(void) { return g_abs_floor2; }
+// Host-side validation of a circuit descriptor (synchronous: copies the gate list and the layer table to the host).  The
+// kernels trust the descriptor -- layers of gates on DISJOINT wires (so at most N/2 gates per layer: the shared-memory
+// coefficient buffers are sized for that), wires in range, parameter columns inside the parameter row.
+extern "C" int mcb200_circuit_validate(const mcb200_circuit_t* c) {
+  if (c == nullptr) return set_error("circuit_validate: descriptor is NULL");
+  if (c->n_qubits < 1) return set_error("circuit_validate: n_qubits must be >= 1, got %d", c->n_qubits);
+  if (c->n_gates < 0 || c->n_layers < 0 || c->n_param_cols < 0) return set_error("circuit_validate: negative count");
+  if ((c->scale == nullptr) != (c->bias == nullptr)) return set_error("circuit_validate: scale and bias must be given together");
+  if (c->n_gates == 0) return 0;
+  if (c->gates == nullptr || c->layer_ptr == nullptr) return set_error("circuit_validate: gates/layer_ptr are NULL");
+  std::vector<mcb200_gate_t> gates((size_t)c->n_gates);
+  std::vector<int32_t> ptr((size_t)c->n_layers + 1);
+  if (int rc = check_cuda(cudaMemcpy(gates.data(), c->gates, gates.size() * sizeof(mcb200_gate_t), cudaMemcpyDeviceToHost),
+                          "circuit_validate: copy of the gate list"))
+    return rc;
+  if (int rc = check_cuda(cudaMemcpy(ptr.data(), c->layer_ptr, ptr.size() * sizeof(int32_t), cudaMemcpyDeviceToHost),
+                          "circuit_validate: copy of layer_ptr"))
+    return rc;
+  if (ptr.front() != 0 || ptr.back() != c->n_gates) return set_error("circuit_validate: layer_ptr must run from 0 to n_gates");
+  std::vector<int> owner((size_t)c->n_qubits);
+  bool nn = true;
+  for (int l = 0; l < c->n_layers; ++l) {
+    if (ptr[l + 1] < ptr[l]) return set_error("circuit_validate: layer_ptr is not monotone at layer %d", l);
+    std::fill(owner.begin(), owner.end(), -1);
+    for (int g = ptr[l]; g < ptr[l + 1]; ++g) {
+      const mcb200_gate_t& t = gates[(size_t)g];
+      if (t.kind < MCB200_GATE_RXRX || t.kind > MCB200_GATE_BLOCK4_PARAM) return set_error("circuit_validate: gate %d has unknown kind %d", g, t.kind);
+      if (t.wire0 < 0 || t.wire1 <= t.wire0 || t.wire1 >= c->n_qubits)
+        return set_error("circuit_validate: gate %d acts on wires (%d, %d) outside 0 <= wire0 < wire1 < %d", g, t.wire0, t.wire1, c->n_qubits);
+      if (t.kind != MCB200_GATE_FSWAP && t.wire1 != t.wire0 + 1)
+        return set_error("circuit_validate: gate %d: two-qubit blocks act on consecutive wires", g);
+      if (t.wire1 != t.wire0 + 1) nn = false;
+      const int width = t.kind <= MCB200_GATE_RZRZ ? 2 : (t.kind == MCB200_GATE_BLOCK4_PARAM ? 16 : 0);
+      if (t.off < 0 || (width && t.off + width > c->n_param_cols))
+        return set_error("circuit_validate: gate %d reads parameter columns [%d, %d) of %d", g, t.off, t.off + width, c->n_param_cols);
+      if (t.kind == MCB200_GATE_BLOCK4_CONST && c->consts == nullptr) return set_error("circuit_validate: gate %d needs consts", g);
+      for (int w = t.wire0; w <= t.wire1; ++w) {
+        if (owner[(size_t)w] >= 0)
+          return set_error("circuit_validate: gates %d and %d of layer %d share wire %d (layers hold gates on disjoint wires)", owner[(size_t)w], g, l, w);
+        owner[(size_t)w] = g;
+      }
+    }
+  }
+  if (c->nearest_neighbour && !nn) return set_error("circuit_validate: nearest_neighbour is set but a gate acts on distant wires");
+  return 0;
+}
+
 extern "C" int mcb200_set_expval_route(int32_t route) {
   if (route < 0 || route > 2) return set_error("set_expval_route: route must be 0 (auto), 1 (columns) or 2 (covariance)");
   g_expval_route = route;

@@ -197,6 +197,25 @@ __global__ void cov_basis_backward_kernel(const double* __restrict__ X, const in
   }
 }
 
+// Shapes whose panels exceed shared memory (full-register gradients beyond ~60 qubits): same arithmetic straight from
+// global memory / L2, Y = G^T - G formed on the fly.  One block per instance.
+__global__ void cov_basis_backward_global_kernel(const double* __restrict__ X, const int8_t* bits, int n_qubits, int m,
+                                                 const double* __restrict__ gcov, double* __restrict__ gX) {
+  const int d = 2 * n_qubits;
+  const long long b = blockIdx.x;
+  const double* src = X + b * (long long)d * m;
+  const double* g = gcov + b * (long long)m * m;
+  double* out = gX + b * (long long)d * m;
+  for (int e = threadIdx.x; e < d * m; e += blockDim.x) {
+    const int r = e / m, c = e - r * m, k = r >> 1;
+    const double sg = (bits != nullptr && bits[k]) ? 1.0 : -1.0;
+    const double* xo = src + (long long)(r ^ 1) * m;
+    double s = 0.0;
+    for (int a = 0; a < m; ++a) s = fma(xo[a], g[(long long)c * m + a] - g[(long long)a * m + c], s);
+    out[e] = (r & 1) ? -sg * s : sg * s;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- K1 adjoint
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -399,7 +418,10 @@ extern "C" int mcb200_cov_basis_backward(const double* X, const int8_t* bits, in
   if (X == nullptr || grad_cov == nullptr || grad_X == nullptr) return set_error("cov_basis_backward: NULL pointer");
   const int d = 2 * n_qubits;
   const size_t smem = ((size_t)d * m + (size_t)m * (m | 1)) * sizeof(double);
-  if (smem > (size_t)kMaxDynSmem) return set_error("cov_basis_backward: d=%d m=%d does not fit shared memory", d, m);
+  if (smem > (size_t)kMaxDynSmem) {
+    cov_basis_backward_global_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(X, bits, n_qubits, m, grad_cov, grad_X);
+    return check_launch("cov_basis_backward_global_kernel");
+  }
   if (int rc = check_cuda(cudaFuncSetAttribute(cov_basis_backward_kernel,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                           "cudaFuncSetAttribute(cov_basis_backward)"))

@@ -132,6 +132,10 @@ class CompiledCircuit:
     def d(self) -> int:
         return 2 * self.n_qubits
 
+    def validate(self) -> None:
+        """Library-side check of the uploaded descriptor (mcb200_circuit_validate); raises Mcb200Error."""
+        check(_lib.load().mcb200_circuit_validate(C.byref(self._struct)))
+
     # ------------------------------------------------------------------ backward light cone of a column panel
     def light_cone_gates(self, cols: Sequence[int]) -> List[GateSpec]:
         """Gates that can influence the columns ``cols`` of the SPTM.  X = G_0 (G_1 (... (G_{n-1} I[:, cols]))) is built

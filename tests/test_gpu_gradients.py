@@ -372,3 +372,28 @@ def test_kernel_alignment_gradient_and_ascent():
         k2.float32_gram = False
         final = float(k2.kernel_alignment(k2(x, x), yc))
     np.testing.assert_allclose(final, k2.opt_.fun, rtol=1e-9)
+
+
+@pytest.mark.parametrize("n,m", [(6, 12), (40, 80), (96, 192)])
+def test_cov_basis_backward_matches_torch_autograd(n, m):
+    """Adjoint of cov = X^T Lambda_0 X: shared-memory kernel and (beyond its panel limit, (96, 192)) the global-memory
+    variant against torch autograd over the same expression."""
+    from matchcake_b200 import ops as mops
+
+    torch.manual_seed(n)
+    B, d = 3, 2 * n
+    x = torch.randn(B, d, m, dtype=torch.float64, device="cuda")
+    bits = torch.randint(0, 2, (n,), device="cuda")
+    w = torch.randn(B, m, m, dtype=torch.float64, device="cuda")
+    xa = x.clone().requires_grad_(True)
+    (mops.cov_basis(xa, n, bits) * w).sum().backward()
+    xb = x.clone().requires_grad_(True)
+    sg = (bits.double() * 2 - 1)                                      # +1 for bit 1, -1 for bit 0
+    lam0 = torch.zeros(d, d, dtype=torch.float64, device="cuda")
+    ev = torch.arange(0, d, 2, device="cuda")
+    lam0[ev, ev + 1] = sg
+    lam0[ev + 1, ev] = -sg
+    ref = xb.transpose(1, 2) @ lam0 @ xb
+    np.testing.assert_allclose(mops.cov_basis(x, n, bits).cpu().numpy(), ref.detach().cpu().numpy(), rtol=1e-12, atol=1e-12)
+    (ref * w).sum().backward()
+    np.testing.assert_allclose(xa.grad.cpu().numpy(), xb.grad.cpu().numpy(), rtol=1e-11, atol=1e-11)

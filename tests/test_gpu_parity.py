@@ -739,3 +739,50 @@ def test_fused_circuit_cov_basis_matches_two_kernels_and_oracle(n, depth, cols, 
         f2 = mops.circuit_cov_basis(circ2, p, cols, torch.as_tensor(bits))
         t2 = mops.cov_basis(mops.circuit_columns(circ2, p, cols), n, torch.as_tensor(bits))
         np.testing.assert_allclose(f2.cpu().numpy(), t2.cpu().numpy(), rtol=1e-13, atol=1e-15)
+
+
+def test_circuit_validate_accepts_good_and_rejects_malformed_descriptors():
+    """mcb200_circuit_validate: what a non-Python host calls once per circuit structure (the kernels trust
+    layer_ptr / wires; a malformed descriptor must be caught at the boundary, not corrupt shared memory)."""
+    import ctypes as C
+
+    from matchcake_b200 import _lib
+    from matchcake_b200 import ops as mops
+    from matchcake_b200._lib import Mcb200Error
+
+    g = [mops.GateSpec(mops.GATE_RXRX, 0, 1, 0), mops.GateSpec(mops.GATE_RYRY, 2, 3, 2), mops.GateSpec(mops.GATE_FSWAP, 1, 2),
+         mops.GateSpec(mops.GATE_FSWAP, 0, 3, 0, mops.FLAG_TRANSPOSE)]
+    circ = mops.CompiledCircuit(4, g, 4)
+    circ.validate()
+    lib = _lib.load()
+
+    def broken(mutate, match):
+        c2 = mops.CompiledCircuit(4, g, 4)
+        mutate(c2)
+        with pytest.raises(Mcb200Error, match=match):
+            c2.validate()
+
+    def share_wire(c2):   # two gates on wire 1 in one layer
+        c2.layer_ptr_dev.copy_(torch.tensor([0, 3, 3, 4], dtype=torch.int32))
+    broken(share_wire, "share wire")
+
+    def wire_out_of_range(c2):
+        arr = c2.gates_dev.clone()
+        arr[1, 2] = 7
+        c2.gates_dev.copy_(arr)
+    broken(wire_out_of_range, "outside")
+
+    def param_overrun(c2):
+        arr = c2.gates_dev.clone()
+        arr[1, 3] = 3
+        c2.gates_dev.copy_(arr)
+    broken(param_overrun, "parameter columns")
+
+    def bad_ptr(c2):
+        c2.layer_ptr_dev.copy_(torch.tensor([0, 2, 1, 4], dtype=torch.int32))
+    broken(bad_ptr, "monotone|share wire")
+
+    def lying_flag(c2):
+        c2._struct.nearest_neighbour = 1
+    broken(lying_flag, "nearest_neighbour")
+    assert lib.mcb200_circuit_validate(None) != 0
