@@ -263,7 +263,10 @@ __global__ void __launch_bounds__(128) probs_tree_kernel(const double* __restric
     double* cur = bufA; double* nxt = bufB; double* fc = fA; double* fn = fB;
     for (int j = 0; j < k; ++j) {
       const int s = m - 2 * j, s2 = s - 2, nodes = 1 << j;
-      const int ss = s * s, ss2 = s2 * s2;
+      // node strides padded to odd: with lanes over the children (deep levels) consecutive parents / children then fall
+      // into different banks (unpadded, 16 x 16 or 64 doubles apart, they all hit one: ncu counted 61 % of the kernel's
+      // shared-memory wavefronts as conflicts)
+      const int ss = (s * s) | 1, ss2 = (s2 * s2) | 1, ne2 = s2 * s2;
       // children c = 2 * node + y
       for (int c = lane; c < 2 * nodes; c += 32) {
         const double* T = cur + (size_t)(c >> 1) * ss;
@@ -273,14 +276,14 @@ __global__ void __launch_bounds__(128) probs_tree_kernel(const double* __restric
       }
       __syncwarp();
       if (s2 > 0) {
-        if (ss2 >= 64) {  // lanes over the elements of one child
+        if (ne2 >= 64) {  // lanes over the elements of one child
           for (int c = 0; c < 2 * nodes; ++c) {
             const double* T = cur + (size_t)(c >> 1) * ss;
             double* U = nxt + (size_t)c * ss2;
             const double piv = T[1] + ((c & 1) ? 1.0 : -1.0);
             const bool dead = fn[c] == 0.0;
             const double inv = dead ? 0.0 : 1.0 / piv;
-            for (int e = lane; e < ss2; e += 32) {
+            for (int e = lane; e < ne2; e += 32) {
               const int ra = e / s2, rb = e - ra * s2;
               if (rb > ra) {
                 const double ta = T[ra + 2] * inv, tb = T[rb + 2] * inv;          // tau = T[0][.] / piv
@@ -326,9 +329,9 @@ __global__ void __launch_bounds__(128) probs_tree_kernel(const double* __restric
 
 int tiles_probs_all(const double* cov, long long B, int k, int normalize, double* out, cudaStream_t st) {
   const int m = 2 * k;
-  size_t buf = (size_t)m * m;
+  size_t buf = (size_t)m * m + 1;
   for (int j = 0; j <= k; ++j) {
-    const size_t w = ((size_t)1 << j) * (size_t)(m - 2 * j) * (m - 2 * j);
+    const size_t w = ((size_t)1 << j) * (((size_t)(m - 2 * j) * (m - 2 * j)) | 1);  // padded node stride, see the kernel
     if (w > buf) buf = w;
   }
   const size_t per_warp = (2 * buf + 2 * ((size_t)1 << k)) * sizeof(double);

@@ -22,7 +22,7 @@ python - <<PY
 import json
 for f in ("$O/bench_default_n$N.json", "$O/bench_c5_n$N.json"):
     try:
-        d = json.load(open(f))
+        d = json.loads([l for l in open(f).read().splitlines() if l.startswith("{")][-1])
         g = d.get("gram")
         print(f, d["n_gpus"], round(d["ms_per_step"], 4), d["value"], "gram", None if g is None else (round(g["ms_per_step"], 2), g["value"], g.get("stages_ms_rank0")))
     except Exception as e:
