@@ -167,7 +167,9 @@ def _majorana2() -> np.ndarray:
 
 
 def matchgate_to_sptm_block(u: np.ndarray) -> np.ndarray:
-    """(..., 4, 4) complex matchgate -> (..., 4, 4) real SPTM block.  Host-side (tiny, per distinct gate)."""
+    """(..., 4, 4) complex matchgate -> (..., 4, 4) real SPTM block on the HOST: only for constants that are baked into a
+    circuit descriptor once (the Hadamard entangler block of FermionicPQCKernel); batched / runtime matchgates go through
+    the ``mcb200_matchgate_sptm`` kernel (``ops.matchgate_sptm``)."""
     c = _majorana2()
     u = np.asarray(u, dtype=complex)
     uc = np.einsum("...ij,mjq->...miq", u, c)
@@ -640,8 +642,10 @@ class ProductState(Operation):
 
     @property
     def covariance_matrix(self) -> np.ndarray:
-        r"""``(\Lambda_0)_{\mu\nu} = i<c_\mu c_\nu>`` from the Bloch vectors (product_state.py:141-245).  O(n^2)
-        input preparation on the host; the conjugation by the circuit runs on the GPU."""
+        r"""``(\Lambda_0)_{\mu\nu} = i<c_\mu c_\nu>`` from the Bloch vectors (product_state.py:141-245).  Host-side
+        INSPECTION property with the reference's name (O(n^2), numpy); the device never calls it -- its initial covariance
+        comes from the ``mcb200_product_state_cov`` kernel (``ops.product_state_cov``), and this property is what the CPU
+        tests compare that kernel's formula against."""
         x, y, z = self.bloch()
         n = x.shape[-1]
         cov = np.zeros(x.shape[:-1] + (2 * n, 2 * n))
