@@ -294,6 +294,13 @@ int mcb200_sector_features_backward(const double* cov, int64_t B, int32_t D, con
                                     int32_t s, const double* feats, const double* grad_feats, double* grad_cov,
                                     void* stream);
 
+/* Adjoint of mcb200_matchgate_sptm: grad_blocks (B, 4, 4) real -> grad_U (B, 4, 4) complex as interleaved (re, im),
+ * dL/dU = 1/2 sum_{mu nu} grad[mu][nu] c_nu U c_mu (dL/dRe U + i dL/dIm U): gradients w.r.t. the entries of generic
+ * matchgates (the reference differentiates make_single_particle_transition_matrix_from_gate, utils/__init__.py:561-596,
+ * with torch autograd). */
+int mcb200_matchgate_sptm_backward(const double* U_re_im, int64_t B, const double* grad_blocks, double* grad_U_re_im,
+                                   void* stream);
+
 /* Adjoint of mcb200_cov_basis: grad_X = Lambda_0 X (grad_cov^T - grad_cov), X and grad_X (B, 2N, m). */
 int mcb200_cov_basis_backward(const double* X, const int8_t* bits, int64_t B, int32_t n_qubits, int32_t m,
                               const double* grad_cov, double* grad_X, void* stream);

@@ -68,6 +68,7 @@ SIGNATURES = {
     "mcb200_gram_blocks4": (c_i32, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i64, c_i64, c_i32, c_f64, c_vp, c_i64, c_vp]),
     "mcb200_gram_symmetrize": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp]),
     "mcb200_sample": (c_i32, [c_vp, c_i64, c_i32, c_i64, C.c_uint64, c_vp, c_vp, c_vp, c_vp]),
+    "mcb200_matchgate_sptm_backward": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "mcb200_pfaffian_backward": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "mcb200_probs_backward": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "mcb200_sector_features_backward": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),

@@ -72,6 +72,50 @@ __global__ void matchgate_sptm_kernel(const double* __restrict__ U, long long B,
     atomicMax(max_imag_bits, (unsigned long long)__double_as_longlong(worst));  // non-negative doubles order like ints
 }
 
+// Adjoint of matchgate_sptm_kernel: with g = dL/dR (real 4 x 4),  dL/dU = 1/2 sum_{mu nu} g[mu][nu] c_nu U c_mu  (torch's
+// convention for a real loss of a complex tensor: dL/dRe U + i dL/dIm U).  (c_nu U c_mu)[i][j] = ph_nu[i] U[perm_nu[i]][perm_mu[j]]
+// ph_mu[perm_mu[j]] because the two-qubit Majoranas are phased involutive permutations.
+__global__ void matchgate_sptm_backward_kernel(const double* __restrict__ U, long long B, const double* __restrict__ gR,
+                                               double* __restrict__ gU) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  cplx u[4][4];
+  const double* p = U + b * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[i][j] = {p[(i * 4 + j) * 2], p[(i * 4 + j) * 2 + 1]};
+  cplx acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = {0.0, 0.0};
+  const double* g = gR + b * 16;
+#pragma unroll
+  for (int mu = 0; mu < 4; ++mu)
+#pragma unroll
+    for (int nu = 0; nu < 4; ++nu) {
+      const double w = 0.5 * g[mu * 4 + nu];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = kMajPerm[nu][i], l = kMajPerm[mu][j];
+          const cplx t = cmul(cmul({kMajPh[nu][i][0], kMajPh[nu][i][1]}, u[k][l]), {kMajPh[mu][l][0], kMajPh[mu][l][1]});
+          acc[i][j].re += w * t.re;
+          acc[i][j].im += w * t.im;
+        }
+    }
+  double* o = gU + b * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[(i * 4 + j) * 2] = acc[i][j].re;
+      o[(i * 4 + j) * 2 + 1] = acc[i][j].im;
+    }
+}
+
 // One block per product state: amplitudes (n, 2) complex as (re, im) pairs -> cov (D x D), D = 2n (+1 if extended).
 __global__ void product_state_cov_kernel(const double* __restrict__ amp, int n, int extended, double* __restrict__ cov) {
   extern __shared__ double sh[];  // x[n] | y[n] | z[n]
@@ -128,6 +172,17 @@ extern "C" int mcb200_matchgate_sptm(const double* U_re_im, int64_t B, double* b
   matchgate_sptm_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(U_re_im, B, blocks_out,
                                                                     reinterpret_cast<unsigned long long*>(max_imag_out));
   return check_launch("matchgate_sptm_kernel");
+}
+
+extern "C" int mcb200_matchgate_sptm_backward(const double* U_re_im, int64_t B, const double* grad_blocks,
+                                              double* grad_U_re_im, void* stream) {
+  if (B < 0) return set_error("matchgate_sptm_backward: negative batch");
+  if (B == 0) return 0;
+  if (U_re_im == nullptr || grad_blocks == nullptr || grad_U_re_im == nullptr)
+    return set_error("matchgate_sptm_backward: NULL pointer");
+  matchgate_sptm_backward_kernel<<<(unsigned)((B + 127) / 128), 128, 0, as_stream(stream)>>>(U_re_im, B, grad_blocks,
+                                                                                             grad_U_re_im);
+  return check_launch("matchgate_sptm_backward_kernel");
 }
 
 extern "C" int mcb200_product_state_cov(const double* amplitudes_re_im, int64_t B, int32_t n_qubits, int32_t extended,

@@ -453,7 +453,8 @@ class NonInteractingFermionicDevice(PennyLaneDeviceMixin):
                 span = make_wires_continuous(idx)
                 if len(span) == 2 and idx[0] < idx[1]:
                     mt = _as_f64_tensor(m)
-                    if mt.ndim == 2:
+                    wants_grad = isinstance(m, torch.Tensor) and m.requires_grad and torch.is_grad_enabled()
+                    if mt.ndim == 2 and not wants_grad:
                         gates.append(_ops.GateSpec(_ops.GATE_BLOCK4_CONST, idx[0], idx[1], len(consts)))
                         consts.extend(mt.reshape(-1).tolist())
                     else:

@@ -105,6 +105,9 @@ class MatchgateOperation(Operation):
             raise AssertionError(f"MatchgateOperation requires consecutive wires, got {self.wires}.")
         m = matrix.detach().cpu().numpy() if isinstance(matrix, torch.Tensor) else np.asarray(matrix)
         self._matrix = m.astype(complex)
+        #: the caller's tensor when it takes part in autograd: the SPTM block is then derived from IT (mcb200_matchgate_sptm
+        #: and its adjoint kernel), so gradients reach the parameters the matchgate was built from
+        self._matrix_t = matrix if (isinstance(matrix, torch.Tensor) and matrix.requires_grad) else None
         if self._matrix.shape[-2:] != (4, 4):
             raise ValueError(f"Matchgate matrix must be (..., 4, 4), got {self._matrix.shape}")
         self.kwargs = kwargs
@@ -137,6 +140,8 @@ class MatchgateOperation(Operation):
     def single_particle_transition_matrix(self):
         r"""``R_{\mu\nu} = 1/4 Tr(U c_\mu U^\dagger c_\nu)`` (utils/__init__.py:561-596), real (…, 4, 4).  Computed by the
         CUDA library (``mcb200_matchgate_sptm``); raises ``ValueError`` if the imaginary part exceeds 1e-6."""
+        if self._matrix_t is not None and torch.is_grad_enabled():
+            return _ops.matchgate_sptm(self._matrix_t.to("cuda"))
         return _ops.matchgate_sptm(torch.as_tensor(self._matrix).to("cuda"))
 
     def to_sptm_operation(self) -> "SingleParticleTransitionMatrixOperation":
@@ -149,6 +154,11 @@ class MatchgateOperation(Operation):
             raise ValueError(f"Cannot multiply MatchgateOperation with {type(other)}")
         if self.wires != other.wires:
             return self.to_sptm_operation() @ other.to_sptm_operation()
+        if self._matrix_t is not None or other._matrix_t is not None:   # keep the product inside autograd
+            a = self._matrix_t if self._matrix_t is not None else torch.as_tensor(self._matrix)
+            b = other._matrix_t if other._matrix_t is not None else torch.as_tensor(other._matrix)
+            return MatchgateOperation(a.to(torch.complex128) @ b.to(device=a.device, dtype=torch.complex128),
+                                      wires=self.wires, check=False)
         return MatchgateOperation(self._matrix @ other._matrix, wires=self.wires, check=False)
 
 

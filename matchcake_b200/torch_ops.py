@@ -307,6 +307,34 @@ def _(u_re_im):
     return u_re_im.new_empty((u_re_im.shape[0], 4, 4), dtype=torch.float64), u_re_im.new_empty((1,), dtype=torch.float64)
 
 
+@_define("matchgate_sptm_backward", "(Tensor u_re_im, Tensor grad_blocks) -> Tensor")
+def _matchgate_sptm_backward(u_re_im, grad_blocks):
+    ur, g = _d(u_re_im, "u_re_im"), _d(grad_blocks, "grad_blocks")
+    gu = torch.empty_like(ur)
+    check(_lib.load().mcb200_matchgate_sptm_backward(_p(ur), ur.shape[0], _p(g), _p(gu), _stream()))
+    return gu
+
+
+@_fake("matchgate_sptm_backward")
+def _(u_re_im, grad_blocks):
+    return u_re_im.new_empty(u_re_im.shape, dtype=torch.float64)
+
+
+def _mg_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0].detach())
+    ctx.set_materialize_grads(False)
+
+
+def _mg_backward(ctx, g_blocks, g_worst):
+    (ur,) = ctx.saved_tensors
+    if g_blocks is None:
+        return None
+    return torch.ops.mcb200.matchgate_sptm_backward(ur, g_blocks.to(torch.float64).contiguous())
+
+
+_tl.register_autograd(f"{NS}::matchgate_sptm", _mg_backward, setup_context=_mg_setup)
+
+
 @_define("product_state_cov", "(Tensor amplitudes_re_im, bool extended) -> Tensor")
 def _product_state_cov(amp, extended):
     """(B, n, 2, 2) interleaved complex per-qubit amplitudes -> (B, D, D), D = 2n (+1 if extended)."""

@@ -22,7 +22,7 @@ ENTRY_TO_OP = {
     "mcb200_circuit_expval_projector": "circuit_expval_projector", "mcb200_circuit_cov_basis": "circuit_cov_basis", "mcb200_gram": "gram_out",
     "mcb200_circuit_pair_blocks": "circuit_pair_blocks", "mcb200_gram_blocks4": "gram_blocks4_out",
     "mcb200_gram_symmetrize": "gram_symmetrize_", "mcb200_sample": "sample",
-    "mcb200_pfaffian_backward": "pfaffian_backward", "mcb200_probs_backward": "probs_backward",
+    "mcb200_matchgate_sptm_backward": "matchgate_sptm_backward", "mcb200_pfaffian_backward": "pfaffian_backward", "mcb200_probs_backward": "probs_backward",
     "mcb200_sector_features_backward": "sector_features_backward", "mcb200_cov_basis_backward": "cov_basis_backward",
     "mcb200_cov_dense_backward": "cov_dense_backward", "mcb200_circuit_columns_backward": "circuit_columns_backward",
 }
