@@ -88,13 +88,13 @@ def folded_rows_in_place(compute_rows: Callable[[int, int, torch.Tensor], None],
     mark("begin")
     compute_rows(t0, t1, k[t0:t1])
     mark("top_rows")
-    # the (short) top block is exchanged while the (long) bottom block is being computed: the collective runs on NCCL's
-    # own stream behind the top kernel; in place -- slot `rank` of the output is the input
-    top = dist.all_gather_into_tensor(k[: n // 2], k[t0:t1], async_op=True)
     compute_rows(b0, b1, k[b0:b1])
     mark("bottom_rows")
+    # Both exchanges AFTER both kernels.  Measured at N = 8 (C3): issuing the top block's all-gather asynchronously under
+    # the bottom kernel made the step 47.0 ms instead of 37.1 -- the collective's kernel holds SMs while it waits for the
+    # slowest peer, and the persistent one-block-per-SM Gram grid then runs its share of those SMs' work late.
+    dist.all_gather_into_tensor(k[: n // 2], k[t0:t1])                      # in place: slot `rank` is the input
     dist.all_gather([k[n - (r + 1) * h: n - r * h] for r in range(ws)], k[b0:b1])
-    top.wait()
     mark("all_gather")
     return k
 
