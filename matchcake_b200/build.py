@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcb200.so")
 SOURCES = ["api.cu", "circuit.cu", "circuit_brick.cu", "circuit_panel.cu", "pfaffian.cu", "pfaffian_tiles.cu", "pfaffian_block_tiles.cu", "pfaffian_panel.cu", "expval_warp.cu", "expval_cov.cu", "gram_blocks.cu", "prep.cu", "gemm.cu", "backward.cu", "sampling.cu"]
-HEADERS = ["common.cuh", "circuit_dev.cuh", "pfaffian_src.cuh", "pfaffian_dev.cuh", "pfaffian_tiles.cuh", "pfaffian_block_tiles.cuh", "tiles_api.cuh", os.path.join("..", "..", "include", "mcb200.h")]
+HEADERS = ["common.cuh", "circuit_dev.cuh", "pfaffian_src.cuh", "pfaffian_dev.cuh", "pfaffian_tiles.cuh", "pfaffian_flat.cuh", "pfaffian_block_tiles.cuh", "tiles_api.cuh", os.path.join("..", "..", "include", "mcb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "pfaffian_src.cuh"
 #include "pfaffian_tiles.cuh"
+#include "pfaffian_flat.cuh"
 #include "tiles_api.cuh"
 
 namespace mcb200 {
@@ -173,6 +174,97 @@ __global__ void __launch_bounds__(32 * TI * TJ, MINB) gram_tiles_kernel(GramTile
   }
 }
 
+// ---- full-size matrices (m = 8 MT): branch-free static elimination (pfaffian_flat.cuh) -------------------------------
+// A cell whose guard failed somewhere is redone from its inputs with partial pivoting (out of line: rare).
+template <int MT, int SR>
+__device__ __noinline__ double gram_cell_pivoted(const double2* a, const double2* b, int m, double* scratch, double2* sm) {
+  constexpr int NT = Tiles<MT>::NT;
+  constexpr int SMT = GramSmem<MT, SR>::kSmTiles;
+  double c[NT][2];
+#pragma unroll
+  for (int q = 0; q < NT; ++q) {
+    const double2 x = __ldg(a + q * 32), y = __ldg(b + q * 32);
+    if (q < SMT) {
+      sm[q * 32] = make_double2(x.x + y.x, x.y + y.y);
+    } else {
+      c[q][0] = x.x + y.x;
+      c[q][1] = x.y + y.y;
+    }
+  }
+  __syncwarp();
+  return warp_pfaffian_tiles_pivoted<MT, SR>(c, m, scratch, sm, 0);
+}
+
+struct GramCellWalk {  // the (i, j) cells of one warp, in the order of gram_tiles_kernel
+  long long rb_n, cb_n, total;
+  bool upper;
+  template <int TI, int TJ>
+  __device__ __forceinline__ void init(const GramTileArgs& g) {
+    const long long rows = g.row_end - g.row_begin;
+    rb_n = (rows + TI - 1) / TI;
+    cb_n = (g.n1 + TJ - 1) / TJ;
+    total = rb_n * cb_n;
+    upper = g.n0 < g.n1;  // reference rule: evaluate j > i, else i > j (gram_matrix.py:191-195)
+  }
+  template <int TI, int TJ>
+  __device__ __forceinline__ bool cell(const GramTileArgs& g, long long t, long long& i, long long& j) const {
+    const long long rb = t / cb_n, cb = t - rb * cb_n;
+    const long long i_lo = g.row_begin + rb * TI, j_lo = cb * TJ;
+    if (g.mode != MCB200_GRAM_FULL) {
+      if (!upper && j_lo >= i_lo + TI) return false;
+      if (upper && j_lo + TJ - 1 <= i_lo) return false;
+    }
+    i = i_lo + warp_id() / TJ;
+    j = j_lo + warp_id() % TJ;
+    bool on = i < g.row_end && j < g.n1;
+    if (g.mode != MCB200_GRAM_FULL) on = on && (upper ? (j > i) : (i > j));
+    return on;
+  }
+};
+
+__device__ __forceinline__ void gram_emit(const GramTileArgs& g, long long i, long long j, double pf) {
+  if (lane_id() == 0) {
+    const double v = abs_floor(g.scale * pf, g.floor2);
+    g.K[i * g.ldk + j] = v;
+    if (g.mode == MCB200_GRAM_REFERENCE && j < g.n0 && i < g.n1) g.K[j * g.ldk + i] = v;  // gram_matrix.py:139-143
+  }
+}
+
+// One cell at a time, branch-free steps.
+template <int MT, int SR, int TI, int TJ>
+__global__ void __launch_bounds__(32 * TI * TJ, 1) gram_tiles_flat_kernel(GramTileArgs g) {
+  constexpr int NT = Tiles<MT>::NT;
+  constexpr int SMT = GramSmem<MT, SR>::kSmTiles;
+  extern __shared__ __align__(16) double smem[];
+  double* scratch = smem + (size_t)warp_id() * GramSmem<MT, SR>::kPerWarp;
+  const int lane = lane_id();
+  double2* sm = reinterpret_cast<double2*>(scratch + Tiles<MT>::kScratch) + lane;
+  const StaticLane<MT> L = static_lane_setup<MT>(scratch);
+  GramCellWalk w;
+  w.init<TI, TJ>(g);
+  for (long long t = blockIdx.x; t < w.total; t += gridDim.x) {
+    long long i, j;
+    if (!w.cell<TI, TJ>(g, t, i, j)) continue;
+    const double2* a = g.p0 + i * (long long)(NT * 32) + lane;
+    const double2* b = g.p1 + j * (long long)(NT * 32) + lane;
+    double c[NT][2];
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+      const double2 x = __ldg(a + q * 32), y = __ldg(b + q * 32);
+      if (q < SMT) {
+        sm[q * 32] = make_double2(x.x + y.x, x.y + y.y);
+      } else {
+        c[q][0] = x.x + y.x;
+        c[q][1] = x.y + y.y;
+      }
+    }
+    double pf = 1.0;
+    if (!warp_pfaffian_flat_steps<MT, SR>(c, scratch, sm, pf, L)) pf = gram_cell_pivoted<MT, SR>(a, b, g.m, scratch, sm);
+    gram_emit(g, i, j, pf);
+    __syncwarp();
+  }
+}
+
 long long tiles_gram_workspace_bytes(long long n0, long long n1, int d) {
   if (d > 64) return 0;
   const int mt = d <= 8 ? 1 : d <= 16 ? 2 : d <= 24 ? 3 : d <= 32 ? 4 : d <= 48 ? 6 : 8;
@@ -213,6 +305,12 @@ static int gram_tiles_launch(const double* cov0, const double* cov1, long long n
     // on C3 (round 2, 4 x 4 block pivots): 249.5 ms against 281 ms (two tile-rows in shared memory, 16 warps at 128
     // registers, spills), 270 ms (three tile-rows, 14 warps) and 259 ms (three tile-rows, 16 warps): more resident warps
     // do not pay for the shared-memory traffic of the tiles they evict from the registers.
+    // full 64 x 64 matrices: branch-free steps, 8 warps per SM with every tile in registers (255): 57.3 ms against
+    // 61.9 ms on a 4096-sample Gram of config C3 (59.6 ms at 12 warps / 168 registers).  MCB200_GRAM_FLAT=0 selects the
+    // one-branch-per-quadruple kernel below (A/B measurements, scripts/gram_flat_check.py).
+    const char* env = getenv("MCB200_GRAM_FLAT");
+    if (d == 8 * MT && (env == nullptr || atoi(env) != 0))
+      return launch(gram_tiles_flat_kernel<MT, 0, 2, 4>, 2, 4, 1, GramSmem<MT, 0>::kPerWarp);
     return launch(gram_tiles_kernel<MT, 1, 3, 4, 1>, 3, 4, 1, GramSmem<MT, 1>::kPerWarp);
   } else {
     return launch(gram_tiles_kernel<MT, 0, 2, 8, 1>, 2, 8, 2, GramSmem<MT, 0>::kPerWarp);

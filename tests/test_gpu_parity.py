@@ -526,6 +526,39 @@ def test_gram_matches_reference_formulation(n, shape):
         mops.gram(dev(c0), dev(c1), scale=1.0, row_range=(0, h), out=final[:h], rows_only=True)  # REFERENCE mirrors outside
 
 
+def test_gram_full_size_cells_whose_static_guard_fails():
+    """64 x 64 cells go through the branch-free static elimination (pfaffian_flat.cuh): a failed block-pivot guard is
+    only recorded and the cell is redone from its inputs with partial pivoting.  Force the failure at every quadruple
+    (zero and tiny leading 4 x 4 blocks of the Schur complement) next to ordinary cells and compare every entry with
+    the oracle's Pfaffian of the sum."""
+    from matchcake_b200 import ops as mops
+
+    d, n0, n1 = 64, 20, 19
+    rng = np.random.default_rng(64)
+    a = random_skew(rng, (n0, d, d)) / 4.0
+    b = random_skew(rng, (n1, d, d)) / 4.0
+    case = 0
+    for s in range(0, d // 4):
+        for eps in (0.0, 1e-9):
+            i, j = case % n0, case % n1
+            case += 1
+            sm = a[i] + b[j]
+            r = 4 * s
+            if s == 0:
+                blk = eps * random_skew(rng, (4, 4))
+            else:  # leading block of the Schur complement after eliminating the first r indices
+                lead, off = sm[:r, :r], sm[:r, r:r + 4]
+                blk = eps * random_skew(rng, (4, 4)) - off.T @ np.linalg.inv(lead) @ off
+            b[j][r:r + 4, r:r + 4] = (blk - blk.T) / 2 - a[i][r:r + 4, r:r + 4]
+    out = mops.gram(dev(a), dev(b), scale=1.0, mode=mops.GRAM_FULL).cpu().numpy()
+    ref = np.abs(pfaffian.pfaffian_signed((a[:, None] + b[None, :]).reshape(-1, d, d))).reshape(n0, n1)
+    # the forced cells are ill conditioned on purpose (a vanishing leading block); two pivot orders agree to ~1e-9 there
+    np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-12 * ref.max())
+    ordinary = np.ones((n0, n1), bool)
+    ordinary[np.arange(case) % n0, np.arange(case) % n1] = False
+    np.testing.assert_allclose(out[ordinary], ref[ordinary], rtol=RTOL, atol=ATOL)
+
+
 @pytest.mark.parametrize("shape", [(1, 1), (33, 33), (70, 45), (45, 70), (200, 97), (64, 64)])
 def test_gram_symmetrize_tiles(shape):
     """GramMatrix.symmetrize_ / _fill_diagonal_ (gram_matrix.py:127-161) by the tiled transpose kernel."""
