@@ -532,7 +532,7 @@ def build_workload(name: str, ctx: Ctx):
             return out
 
         w.update(step=step, e2e_step=e2e_step, units=entries, e2e_units=entries, metric="gram_entries_per_sec",
-                 unit="entries/s", scaling="strong", kernel="gram_tiles_kernel<8,1,3,4,1>",
+                 unit="entries/s", scaling="strong", kernel="gram_tiles_flat_kernel<8,0,2,4>",
                  flops_per_launch=gram_flops_per_entry(2 * n) * entries / ws, launches_per_step=None,
                  h2d=ns * 2 * n * 8, d2h=ns * ns * 8, parity=parity, dominant=dominant,
                  stages=stages if ws > 1 else (lambda: None),

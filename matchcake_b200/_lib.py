@@ -12,7 +12,8 @@ import threading
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcb200.so")
+# MCB200_LIB: another build of the same library (A/B measurements of compile-time variants)
+LIB_PATH = os.environ.get("MCB200_LIB") or os.path.join(_HERE, "libmcb200.so")
 
 _lib: Optional[C.CDLL] = None
 _lock = threading.Lock()

@@ -72,7 +72,10 @@ __device__ void build_columns(const CircuitDev& c, const double* prow, const int
     double2* coefB = coefA + coef_cap;
     for (int g = gb + tid; g < ge; g += nthr) {
       const mcb200_gate_t gt = c.gates[g];
-      if (gt.kind <= MCB200_GATE_RZRZ) {
+      // (a layer of more than coef_cap gates -- impossible for gates on disjoint wires, possible in a malformed
+      // descriptor handed over the C ABI -- keeps its surplus gates out of the buffer: they are applied below with
+      // coefficients computed on the fly)
+      if (gt.kind <= MCB200_GATE_RZRZ && g - gb < coef_cap) {
         double cf[4];
         gate_coefficients(c, gt, prow, cf);
         coefA[g - gb] = make_double2(cf[0], cf[1]);
@@ -88,10 +91,14 @@ __device__ void build_columns(const CircuitDev& c, const double* prow, const int
           // lane = gate, all of the warp's columns; neighbouring gates start at staggered columns (bank spread)
           for (int g = lane; g < ng; g += 32) {
             const mcb200_gate_t gt = c.gates[g0 + g];
-            if (gt.kind <= MCB200_GATE_RZRZ) {
-              const int k = g0 + g - gb;
+            const int k = g0 + g - gb;
+            if (gt.kind <= MCB200_GATE_RZRZ && k < coef_cap) {
               apply_rotation_columns<true>(gt.kind, gt.wire0, coefA[k], coefB[k], X, ld, base, 1, wc,
                                            wc_pow2 ? ((g >> 2) & (wc - 1)) : 0);
+            } else if (gt.kind <= MCB200_GATE_RZRZ) {
+              double cf[4];
+              gate_coefficients(c, gt, prow, cf);
+              apply_gate_columns(c, gt, cf, prow, X, ld, base, 1, base + wc);
             } else {
               apply_gate_columns(c, gt, nullptr, prow, X, ld, base, 1, base + wc);
             }

@@ -23,16 +23,6 @@
 
 namespace mcb200 {
 
-// 1 / x for a normal, non-zero x: hardware seed (e = 1 - x y ~ 2^-23) and one cubic step y (1 + e + e^2), relative
-// error e^3 -- three dependent operations after the seed instead of the four of two Newton steps (fast_rcp).
-__device__ __forceinline__ double fast_rcp3(double x) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-x, y, 1.0);
-  const double t = fma(e, e, e);
-  return fma(y, t, y);
-}
-
 // Largest |entry| (as the high word of the double) of rows R .. R+3 over the columns > R; M a multiple of 32.
 template <int M, int R>
 __device__ __forceinline__ unsigned static_rows_max_key_full(const double* scratch) {

@@ -278,6 +278,16 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(y, e, y);
 }
 
+// The same with one cubic step y (1 + e + e^2), e = 1 - x y ~ 2^-20 from the seed: relative error e^3, three dependent
+// operations after the seed instead of four.
+__device__ __forceinline__ double fast_rcp3(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
+}
+
 template <int MT, int SR, int TR, int TJ>
 __device__ __forceinline__ void static_store_rows(const double (&c)[Tiles<MT>::NT][2], const double2* sm, double* dst) {
   if constexpr (TJ < MT) {
@@ -383,6 +393,31 @@ __device__ __forceinline__ int warp_pfaffian_static_steps(double (&c)[Tiles<MT>:
     const double2 de = *reinterpret_cast<const double2*>(v + R + 2);
     const double f = u2[R + 3];
     const double q = fma(a, f, fma(bc.y, de.x, -bc.x * de.y));
+    constexpr int TI0 = (D & 1) ? TR + 1 : TR;  // tile row TR is dead once its second quadruple has been eliminated
+    double af[MT], bf[MT];
+#ifndef MCB200_STATIC_CHAIN_OLD
+    // The chain per quadruple is what bounds the callers (2 - 5 warps per scheduler): the reciprocal (one cubic Newton
+    // step, pfaffian_flat.cuh) does not wait for the guard's branch, |B| is summed as a tree, and the B fragment is
+    // built from the unscaled block entries while the reciprocal is in flight, then multiplied by 1/q -- one more DMUL
+    // per fragment entry, four fewer dependent operations (measured on config C3's Gram kernel: 61.9 -> 59.6 ms).
+    const double invq = fast_rcp3(q);  // q = 0 gives inf / NaN here, which the guard below keeps from being used
+    // guard: growth of the update  ||r||^2 ||B^-1|| / s  <=  s sB / |q|  <=  kStaticBlockGrowth
+    const double sB = ((fabs(a) + fabs(bc.x)) + (fabs(bc.y) + fabs(de.x))) + (fabs(de.y) + fabs(f));  // >= max |B entry|
+    double s = 2.0;
+    if constexpr (!BOUNDED)
+      s = __hiloint2double((int)static_rows_max_key<T::M>(scratch, R) + 0x100, 0);  // >= max |entry| of the four rows
+    const bool ok = fabs(q) * (PHYSICAL ? kStaticBlockGrowthPhysical : kStaticBlockGrowth) >= s * sB && q != 0.0;
+    if (!ok) return R;
+    pf *= q;
+    if (R + 4 >= m) return m;
+    // (3) fragments: A = row R + tg, B = y_tg = (sum_j (+-B entry_j) * row_j) / q
+    const double p0 = L.y_ent[0][R] * L.y_sgn[0], p1 = L.y_ent[1][R] * L.y_sgn[1], p2 = L.y_ent[2][R] * L.y_sgn[2];
+#pragma unroll
+    for (int t = TI0; t < MT; ++t) {
+      af[t] = L.a_vec[8 * t];
+      bf[t] = fma(p0, L.y_vec[0][8 * t], fma(p1, L.y_vec[1][8 * t], p2 * L.y_vec[2][8 * t])) * invq;
+    }
+#else
     // guard: growth of the update  ||r||^2 ||B^-1|| / s  <=  s sB / |q|  <=  kStaticBlockGrowth
     const double sB = fabs(a) + fabs(bc.x) + fabs(bc.y) + fabs(de.x) + fabs(de.y) + fabs(f);  // >= max |B entry|
     double s = 2.0;
@@ -396,13 +431,12 @@ __device__ __forceinline__ int warp_pfaffian_static_steps(double (&c)[Tiles<MT>:
     // (3) fragments: A = row R + tg, B = y_tg = sum_j coef_j * row_j
     const double k0 = L.y_ent[0][R] * (L.y_sgn[0] * invq), k1 = L.y_ent[1][R] * (L.y_sgn[1] * invq),
                  k2 = L.y_ent[2][R] * (L.y_sgn[2] * invq);
-    constexpr int TI0 = (D & 1) ? TR + 1 : TR;  // tile row TR is dead once its second quadruple has been eliminated
-    double af[MT], bf[MT];
 #pragma unroll
     for (int t = TI0; t < MT; ++t) {
       af[t] = L.a_vec[8 * t];
       bf[t] = fma(k0, L.y_vec[0][8 * t], fma(k1, L.y_vec[1][8 * t], k2 * L.y_vec[2][8 * t]));
     }
+#endif
     if constexpr (!(D & 1)) {
       if (gr <= ((R + 3) & 7)) af[TR] = bf[TR] = 0.0;  // indices <= R+3 are dead: they neither change nor contribute
     }

@@ -29,7 +29,7 @@ cap() {  # cap <name> <kernel regex> <skip> <target args...>
 }
 if has ncu; then
   cap c2_expval_cov        'expval_cov_kernel'            2 c2
-  cap c3_gram_tiles        'gram_tiles_kernel'            1 gram 2048
+  cap c3_gram_tiles        'gram_tiles'                   1 gram 2048
   cap c4_circuit_columns   'circuit_columns'              1 c4 16384
   cap c4_cov_basis         'cov_basis_kernel'             1 c4 16384
   cap c4_probs_tree        'probs_tree_kernel'            1 c4 16384

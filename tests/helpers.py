@@ -53,3 +53,38 @@ def readme_ops(n, params, matchgate=True):
 def random_skew(rng, shape):
     a = rng.standard_normal(shape)
     return a - np.swapaxes(a, -1, -2)
+
+
+# ------------------------------------------------------------------ dense state-vector simulation (2^n amplitudes)
+# The reference's own tests compare the device with qml.device("default.qubit") on small circuits
+# (tests/test_devices/test_nif_device/test_multiples_matchgate_circuit.py:66-102).  PennyLane is not
+# installed here, so this is the same check by hand: apply the complex 4 x 4 matchgates (oracle.gates.Op.matchgate_matrix:
+# comp_rotations.py:47-80, fermionic_swap.py:15-52) to the 2^n state vector, wire 0 = most significant bit
+# (PennyLane's convention, the one states_to_binary follows, nif_device.py:151-165).
+_SPTM_TO_MATCHGATE = {"SptmCompRxRx": "CompRxRx", "SptmCompRyRy": "CompRyRy", "SptmCompRzRz": "CompRzRz",
+                      "SptmFSwap": "fSWAP"}
+
+
+def statevector(ops, n_wires, init_bits=None):
+    """U |init_bits> as a (2,) * n_wires array for a list of unbatched Ops on ADJACENT wire pairs.  SPTM-flavoured
+    rotations / fSWAPs are simulated as the matchgates they are the single-particle picture of."""
+    psi = np.zeros((2,) * n_wires, dtype=complex)
+    psi[tuple(int(b) for b in (init_bits if init_bits is not None else [0] * n_wires))] = 1.0
+    for op in ops:
+        if op.kind in _SPTM_TO_MATCHGATE:
+            op = Op(_SPTM_TO_MATCHGATE[op.kind], op.wires, params=op.params)
+        w0, w1 = op.wires
+        assert w1 == w0 + 1, "adjacent wires only"
+        u = np.asarray(op.matchgate_matrix(), dtype=complex).reshape(2, 2, 2, 2)   # (out0, out1, in0, in1)
+        psi = np.moveaxis(np.tensordot(u, psi, axes=([2, 3], [w0, w1])), (0, 1), (w0, w1))
+    return psi
+
+
+def statevector_probs(ops, n_wires, init_bits=None, wires=None):
+    """Outcome probabilities of ``wires`` (default: all), shape (2^k,), MSB first in the order the wires are given."""
+    p = np.abs(statevector(ops, n_wires, init_bits)) ** 2
+    if wires is not None:
+        keep = list(wires)
+        p = p.sum(axis=tuple(i for i in range(n_wires) if i not in keep))
+        p = np.transpose(p, np.argsort(np.argsort(keep)))  # axes in the order the wires were given
+    return p.reshape(-1)

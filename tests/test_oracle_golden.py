@@ -233,3 +233,60 @@ def test_gram_identity_covariance_sum():
     lam = cv.evolve(lam0, s)
     alt = 2.0 ** -n * np.abs(pfaffian.pfaffian_signed(lam[idx[:, 0]] + lam[idx[:, 1]]))
     np.testing.assert_allclose(ref, alt, atol=1e-13)
+
+
+# ------------------------------------------------------------------ dense state-vector simulation
+def _random_matchgate_circuit(rng, n, n_gates):
+    ops = []
+    for _ in range(n_gates):
+        w = int(rng.integers(0, n - 1))
+        kind = ("CompRxRx", "CompRyRy", "CompRzRz", "fSWAP")[int(rng.integers(0, 4))]
+        ops.append(gates.Op(kind, (w, w + 1), params=None if kind == "fSWAP" else rng.uniform(0, 2 * np.pi, 2)))
+    return ops
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7])
+def test_oracle_probabilities_equal_dense_statevector(n):
+    """The reference pins its device against qml.device("default.qubit") on small circuits
+    (tests/test_devices/test_nif_device/test_multiples_matchgate_circuit.py:66-102,
+    test_product_state_strategy.py:50-61).  Same check for the oracle, with a hand-written 2^n state-vector simulation
+    of the complex matchgates (tests/helpers.py): full distributions, marginals (in both wire orders) and single
+    outcomes, from random basis states."""
+    from tests.helpers import statevector_probs
+
+    rng = np.random.default_rng(100 + n)
+    for _ in range(3):
+        ops = _random_matchgate_circuit(rng, n, 4 * n)
+        init = rng.integers(0, 2, n)
+        r = gates.chain(ops, n)
+        amp = cv.amplitudes_from_basis_state(init)
+        for wires in (list(range(n)), [0], [n - 1], [n - 1, 0], list(range(n))[::2]):
+            ref = statevector_probs(ops, n, init, wires)
+            got = readout.analytic_probability(r, amp, wires).reshape(-1)
+            np.testing.assert_allclose(got, ref, rtol=0, atol=5e-14)
+        # the two probability strategies of the device on one outcome (lookup table / product-state formula)
+        tgt = rng.integers(0, 2, n)
+        ref = statevector_probs(ops, n, init)[int("".join(map(str, tgt)), 2)]
+        np.testing.assert_allclose(readout.probs_lookup_table(r, init, tgt, np.arange(n)), ref, rtol=0, atol=5e-14)
+        cov_t = cv.evolve(cv.covariance_matrix(amp), r)
+        np.testing.assert_allclose(readout.probs_product_state(cov_t, tgt, np.arange(n)), ref, rtol=0, atol=5e-14)
+
+
+@pytest.mark.parametrize("n,rotations,nf", [(4, "X,Z", 8), (4, "Y,Z", 8), (6, "X,Y,Z", 6), (4, "Z", 4)])
+def test_oracle_kernel_equals_dense_statevector_kernel(n, rotations, nf):
+    """tests/test_ml/test_kernels/test_fermionic_pqc_kernel.py:122-129: the fermionic kernel equals the fidelity kernel
+    |<psi(x_j)|psi(x_i)>|^2 of the same ansatz simulated on a dense state vector."""
+    from tests.helpers import statevector
+
+    rng = np.random.default_rng(n * 7 + nf)
+    x = rng.random((5, nf))
+    k = kernels.FermionicPQCKernelOracle(n_qubits=n, rotations=rotations).fit(x)
+    got = k.gram(x, float32_store=False)
+
+    def unbatched(ops, i):
+        return [gates.Op(o.kind, o.wires, params=None if o.params is None else np.asarray(o.params)[i]) for o in ops]
+
+    ops = k.ansatz(x)
+    states = [statevector(unbatched(ops, i), n).reshape(-1) for i in range(len(x))]
+    ref = np.array([[abs(np.vdot(a, b)) ** 2 for b in states] for a in states])
+    np.testing.assert_allclose(got, ref, rtol=0, atol=5e-14)
