@@ -92,6 +92,41 @@ def test_probabilities_tutorial_golden():
     assert round(float(dev.get_states_probability(5)), 6) == G["projector_101"]["value"]
 
 
+@pytest.mark.parametrize("n", [2, 3, 5, 6, 8])
+def test_device_probabilities_equal_dense_statevector(n):
+    """The reference's own device tests: the same circuit on qml.device("default.qubit")
+    (tests/test_devices/test_nif_device/test_multiples_matchgate_circuit.py:66-102).  Here the dense side is the
+    hand-written 2^n state-vector simulation of tests/helpers.py: qml.probs over all wires and over marginals (both wire
+    orders), and the projector expectation value, from a random basis state."""
+    from tests.helpers import statevector_probs
+
+    rng = np.random.default_rng(300 + n)
+    classes = {"CompRxRx": CompRxRx, "CompRyRy": CompRyRy, "CompRzRz": CompRzRz}
+    for _ in range(2):
+        ref_ops, dev_ops = [], []
+        init = rng.integers(0, 2, n)
+        dev_ops.append(BasisState(init, wires=range(n)))
+        for _ in range(4 * n):
+            w = int(rng.integers(0, n - 1))
+            kind = ("CompRxRx", "CompRyRy", "CompRzRz", "fSWAP")[int(rng.integers(0, 4))]
+            if kind == "fSWAP":
+                ref_ops.append(Op(kind, (w, w + 1)))
+                dev_ops.append(fSWAP(wires=[w, w + 1]))
+            else:
+                p = rng.uniform(0, 2 * np.pi, 2)
+                ref_ops.append(Op(kind, (w, w + 1), params=p))
+                dev_ops.append(classes[kind](p, wires=[w, w + 1]))
+        dev = mc.NonInteractingFermionicDevice(wires=n)
+        dev.execute_generator(dev_ops, output_type=None, reset=True)
+        for wires in (list(range(n)), [0], [n - 1], [n - 1, 0], list(range(n))[::2]):
+            got = np.asarray(dev.analytic_probability(wires)).reshape(-1)
+            np.testing.assert_allclose(got, statevector_probs(ref_ops, n, init, wires), rtol=0, atol=5e-14)
+        tgt = rng.integers(0, 2, n)
+        v = dev.execute_generator(dev_ops, observable=obs.Projector(tgt, wires=range(n)), output_type="expval", reset=True)
+        ref = statevector_probs(ref_ops, n, init)[int("".join(map(str, tgt)), 2)]
+        np.testing.assert_allclose(float(v), ref, rtol=0, atol=5e-14)
+
+
 def test_expectation_values_tutorial_golden():
     g = G["hamiltonian"]
     h = obs.Hamiltonian(g["coeffs"], [obs.X(0) @ obs.X(1), obs.Y(1) @ obs.Y(2), obs.Z(0) @ obs.Z(1), obs.Y(1) @ obs.X(2),

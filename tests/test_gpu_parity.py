@@ -528,35 +528,48 @@ def test_gram_matches_reference_formulation(n, shape):
 
 def test_gram_full_size_cells_whose_static_guard_fails():
     """64 x 64 cells go through the branch-free static elimination (pfaffian_flat.cuh): a failed block-pivot guard is
-    only recorded and the cell is redone from its inputs with partial pivoting.  Force the failure at every quadruple
-    (zero and tiny leading 4 x 4 blocks of the Schur complement) next to ordinary cells and compare every entry with
-    the oracle's Pfaffian of the sum."""
+    only recorded and the cell is redone from its inputs with partial pivoting.  Physical inputs (covariances
+    Q J Q^T of pure Gaussian states of one parity -- the guard's growth bound assumes them): Lambda_j = S Lambda_i S^T
+    with S = P_4 + R', P_4 X P_4^T = -X for the leading block X of Lambda_i, makes the leading 4 x 4 block of
+    Lambda_i + Lambda_j vanish while the sum stays well conditioned; a further rotation by exp(eps K) makes the block
+    tiny instead (eps = 1e-4: small enough to be a bad pivot, large enough to pass the guard).  Ordinary cells sit next
+    to the forced ones.  Every entry against the oracle's Pfaffian of the sum."""
+    from scipy.linalg import expm, schur
+
     from matchcake_b200 import ops as mops
 
-    d, n0, n1 = 64, 20, 19
+    d, n = 64, 12
     rng = np.random.default_rng(64)
-    a = random_skew(rng, (n0, d, d)) / 4.0
-    b = random_skew(rng, (n1, d, d)) / 4.0
-    case = 0
-    for s in range(0, d // 4):
-        for eps in (0.0, 1e-9):
-            i, j = case % n0, case % n1
-            case += 1
-            sm = a[i] + b[j]
-            r = 4 * s
-            if s == 0:
-                blk = eps * random_skew(rng, (4, 4))
-            else:  # leading block of the Schur complement after eliminating the first r indices
-                lead, off = sm[:r, :r], sm[:r, r:r + 4]
-                blk = eps * random_skew(rng, (4, 4)) - off.T @ np.linalg.inv(lead) @ off
-            b[j][r:r + 4, r:r + 4] = (blk - blk.T) / 2 - a[i][r:r + 4, r:r + 4]
+    j0 = np.kron(np.eye(d // 2), np.array([[0.0, 1.0], [-1.0, 0.0]]))
+
+    def rand_so(k):
+        q, _ = np.linalg.qr(rng.standard_normal((k, k)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        return q
+
+    def flip4(x):  # real Schur form x = O (x1 J + x2 J) O^T  ->  P = O diag(1, -1, 1, -1) O^T, det P = +1
+        _, o = schur(x, output="real")
+        return o @ np.diag([1.0, -1.0, 1.0, -1.0]) @ o.T
+
+    a = np.stack([q @ j0 @ q.T for q in (rand_so(d) for _ in range(n))])
+    b = np.stack([q @ j0 @ q.T for q in (rand_so(d) for _ in range(n))])
+    forced = {}
+    for t, eps in enumerate((0.0, 0.0, 1e-12, 1e-9, 1e-6, 1e-4)):
+        i, j = 2 * t, 2 * t + 1
+        r = np.eye(d)
+        r[:4, :4] = flip4(a[i][:4, :4])
+        r[4:, 4:] = rand_so(d - 4)
+        r = r @ expm(eps * random_skew(rng, (d, d)))
+        b[j] = r @ a[i] @ r.T
+        forced[(i, j)] = eps
+    a, b = (a - a.transpose(0, 2, 1)) / 2, (b - b.transpose(0, 2, 1)) / 2
     out = mops.gram(dev(a), dev(b), scale=1.0, mode=mops.GRAM_FULL).cpu().numpy()
-    ref = np.abs(pfaffian.pfaffian_signed((a[:, None] + b[None, :]).reshape(-1, d, d))).reshape(n0, n1)
-    # the forced cells are ill conditioned on purpose (a vanishing leading block); two pivot orders agree to ~1e-9 there
-    np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-12 * ref.max())
-    ordinary = np.ones((n0, n1), bool)
-    ordinary[np.arange(case) % n0, np.arange(case) % n1] = False
-    np.testing.assert_allclose(out[ordinary], ref[ordinary], rtol=RTOL, atol=ATOL)
+    ref = np.abs(pfaffian.pfaffian_signed((a[:, None] + b[None, :]).reshape(-1, d, d))).reshape(n, n)
+    assert ref.min() > 1e-3                                            # nothing here is (near) singular
+    for (i, j), eps in forced.items():
+        assert np.abs((a[i] + b[j])[:4, :4]).max() <= max(8 * eps, 1e-14)
+    np.testing.assert_allclose(out, ref, rtol=RTOL, atol=0)
 
 
 @pytest.mark.parametrize("shape", [(1, 1), (33, 33), (70, 45), (45, 70), (200, 97), (64, 64)])
