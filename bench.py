@@ -502,6 +502,9 @@ def build_workload(name: str, ctx: Ctx):
         def dominant():
             # rank-local: nothing in here may be a collective
             cov = mops.cov_basis(kern._x_to_sptm(x_dev), kern.n_qubits)
+            # the kernel alone: the route the API's "auto" decision takes on this data (decided here, outside the timing)
+            growth = mops._gram_growth_for(cov, cov, ns * ns, "auto")
+            w["config"]["gram_pivot_growth"] = growth
             if ws > 1:
                 (t0, t1), (b0, b1) = dm.folded_row_blocks(ns, ws)[rank]
                 buf = torch.empty((max(t1 - t0, b1 - b0), ns), dtype=torch.float64, device=dev)
@@ -510,10 +513,10 @@ def build_workload(name: str, ctx: Ctx):
                     for s0, e0 in ((t0, t1), (b0, b1)):
                         if e0 > s0:
                             mops.gram(cov, cov, 2.0 ** -32, mode=mops.GRAM_TRIANGLE, row_range=(s0, e0),
-                                      out=buf[: e0 - s0], rows_only=True)
+                                      out=buf[: e0 - s0], rows_only=True, pivoting=growth)
                 return fn
             out = torch.empty((ns, ns), dtype=torch.float64, device=dev)
-            return lambda: mops.gram(cov, cov, 2.0 ** -32, mode=mops.GRAM_REFERENCE, out=out)
+            return lambda: mops.gram(cov, cov, 2.0 ** -32, mode=mops.GRAM_REFERENCE, out=out, pivoting=growth)
 
         def stages():
             """Per-stage device times of one sharded build (ms, this rank): names the residual next to the kernel."""

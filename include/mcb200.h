@@ -96,6 +96,17 @@ int mcb200_circuit_validate(const mcb200_circuit_t* circuit_host);
 int mcb200_set_abs_floor(double floor2);
 double mcb200_get_abs_floor(void);
 
+/* Accuracy / speed of mcb200_gram for d <= 64, sticky per calling thread.  A Gram cell |Pf(cov0[i] + cov1[j])| is
+ * eliminated in the natural index order with 4 x 4 block pivots as long as a guard bounds the growth of every update by
+ * `growth`; a cell whose guard fails is computed with partial pivoting instead (slower, accuracy of the reference's LU).
+ * The initial value 1e5 is calibrated on the covariances of the reference's kernel ansatz (FermionicPQCKernel,
+ * fermionic_pqc_kernel.py:166-199: shallow light cones; worst relative error measured 1e-14).  For covariances of generic
+ * (Haar-like) Gaussian states the same bound lets relative errors of up to 1e-8 through in about 1 cell in 1000; 1e3 keeps
+ * every cell within 1e-11 of the reference at the price of 10 - 40 % of the cells taking the pivoted route.
+ * matchcake_b200.ops.gram(pivoting="auto") decides per call by evaluating a sample of the cells both ways. */
+int mcb200_set_gram_pivot_growth(double growth);
+double mcb200_get_gram_pivot_growth(void);
+
 /* ------------------------------------------------------------------ K1: SPTM chain */
 /* Columns of the global SPTM of a gate-list circuit: X[b] = R_b[:, cols] (d x m), one instance per
  * batch row of params (B, P).  cols = NULL -> all d columns (X = R).  Replaces the per-gate Python

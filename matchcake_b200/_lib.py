@@ -43,6 +43,8 @@ SIGNATURES = {
     "mcb200_device_count": (c_i32, []),
     "mcb200_set_abs_floor": (c_i32, [c_f64]),
     "mcb200_get_abs_floor": (c_f64, []),
+    "mcb200_set_gram_pivot_growth": (c_i32, [c_f64]),
+    "mcb200_get_gram_pivot_growth": (c_f64, []),
     "mcb200_set_expval_route": (c_i32, [c_i32]),
     "mcb200_circuit_validate": (c_i32, [C.POINTER(CircuitStruct)]),
     "mcb200_circuit_columns": (c_i32, [C.POINTER(CircuitStruct), c_vp, c_i64, c_vp, c_i32, c_vp, c_vp]),

@@ -12,6 +12,7 @@ namespace mcb200 {
 thread_local std::string g_last_error;
 std::atomic<long long> g_launch_count{0};
 thread_local double g_abs_floor2 = 0.0;
+thread_local double g_gram_growth = 1e5;  // kStaticBlockGrowthPhysical
 thread_local int g_expval_route = 0;
 
 int set_error(const char* fmt, ...) {
@@ -87,6 +88,14 @@ extern "C" int mcb200_set_abs_floor(double floor2) {
   return 0;
 }
 extern "C" double mcb200_get_abs_floor(void) { return g_abs_floor2; }
+
+extern "C" int mcb200_set_gram_pivot_growth(double growth) {
+  if (!(growth >= 1.0)) return set_error("set_gram_pivot_growth: growth must be >= 1");
+  g_gram_growth = growth;
+  return 0;
+}
+
+extern "C" double mcb200_get_gram_pivot_growth(void) { return g_gram_growth; }
 // Host-side validation of a circuit descriptor (synchronous: copies the gate list and the layer table to the host).  The
 // kernels trust the descriptor -- layers of gates on DISJOINT wires (so at most N/2 gates per layer: the shared-memory
 // coefficient buffers are sized for that), wires in range, parameter columns inside the parameter row.

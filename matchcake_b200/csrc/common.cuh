@@ -16,6 +16,9 @@ extern std::atomic<long long> g_launch_count;
 // Sticky per-thread option (mcb200_set_abs_floor): every magnitude-type output v (|Pf| x scale, probabilities,
 // projector expectation values, Gram entries) is returned as sqrt(v^2 + floor2).  0 = off.
 extern thread_local double g_abs_floor2;
+// Sticky per-thread option (mcb200_set_gram_pivot_growth): growth bound of the static block pivots of mcb200_gram for
+// d <= 64 (pfaffian_tiles.cuh: kStaticBlockGrowthPhysical = 1e5 by default, kStaticBlockGrowth = 1e3 = strict).
+extern thread_local double g_gram_growth;
 
 int set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);

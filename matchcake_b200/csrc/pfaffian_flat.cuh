@@ -56,9 +56,9 @@ struct FlatStep {
   __device__ static __forceinline__ void store(const double (&c)[T::NT][2], const double2* sm, const StaticLane<MT>& L) {
     if (((lane_id() >> 4) & 1) == (D & 1)) static_store_rows<MT, SR, TR, TR>(c, sm, L.st);
   }
-  // (2) - (4) block pivot, update; returns whether the guard (Lambda_i + Lambda_j: kStaticBlockGrowthPhysical) held
+  // (2) - (4) block pivot, update; returns whether the guard (growth of the update <= `growth`) held
   __device__ static __forceinline__ bool run(double (&c)[T::NT][2], double2* sm, const double* scratch,
-                                             const StaticLane<MT>& L, double& pf) {
+                                             const StaticLane<MT>& L, double& pf, double growth) {
     const double* u = scratch;           // row R      (slot 0)
     const double* v = scratch + 2 * VS;  // row R + 1  (slot 2)
     const double* u2 = scratch + VS;     // row R + 2  (slot 1)
@@ -69,7 +69,7 @@ struct FlatStep {
     const double q = fma(a, f, fma(bc.y, de.x, -bc.x * de.y));
     const double sB = ((fabs(a) + fabs(bc.x)) + (fabs(bc.y) + fabs(de.x))) + (fabs(de.y) + fabs(f));
     const double s = __hiloint2double((int)static_rows_max_key_full<T::M, R>(scratch) + 0x100, 0);
-    const bool ok = fabs(q) * kStaticBlockGrowthPhysical >= s * sB && q != 0.0;
+    const bool ok = fabs(q) * growth >= s * sB && q != 0.0;
     pf *= q;
     if constexpr (kUpdate) {
       const double invq = fast_rcp3(q);
@@ -92,16 +92,16 @@ struct FlatStep {
 // All 2 MT quadruples of one full matrix, no branch.  Returns false when a guard failed (pf and c are then garbage).
 template <int MT, int SR, int D = 0>
 __device__ __forceinline__ bool warp_pfaffian_flat_steps(double (&c)[Tiles<MT>::NT][2], double* scratch, double2* sm,
-                                                         double& pf, const StaticLane<MT>& L) {
+                                                         double& pf, const StaticLane<MT>& L, double growth) {
   if constexpr (D >= 2 * MT) {
     return true;
   } else {
     using S = FlatStep<MT, SR, D>;
     S::store(c, sm, L);
     __syncwarp();
-    const bool ok = S::run(c, sm, scratch, L, pf);
+    const bool ok = S::run(c, sm, scratch, L, pf, growth);
     __syncwarp();
-    return warp_pfaffian_flat_steps<MT, SR, D + 1>(c, scratch, sm, pf, L) && ok;
+    return warp_pfaffian_flat_steps<MT, SR, D + 1>(c, scratch, sm, pf, L, growth) && ok;
   }
 }
 

@@ -118,6 +118,7 @@ struct GramTileArgs {
   double* K;
   long long ldk;
   double floor2;
+  double growth;  // bound of the static block pivots (mcb200_set_gram_pivot_growth)
 };
 
 // One warp per (i, j) cell.  A block of TI x TJ warps walks (row-block, column-block) tiles so that the fragments
@@ -128,7 +129,7 @@ struct GramSmem {
   static constexpr int kPerWarp = Tiles<MT>::kScratch + kSmTiles * 64;                  // doubles
 };
 
-template <int MT, int SR, int TI, int TJ, int MINB>
+template <int MT, int SR, int TI, int TJ, int MINB, bool PHYS = true>
 __global__ void __launch_bounds__(32 * TI * TJ, MINB) gram_tiles_kernel(GramTileArgs g) {
   constexpr int NT = Tiles<MT>::NT;
   constexpr int SMT = GramSmem<MT, SR>::kSmTiles;
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(32 * TI * TJ, MINB) gram_tiles_kernel(GramTile
         c[q][1] = x.y + y.y;
       }
     }
-    const double pf = warp_pfaffian_tiles<MT, SR, false, true>(c, g.m, scratch, sm);  // Lambda_i + Lambda_j
+    // Lambda_i + Lambda_j: growth bound 1e5 (PHYS, calibrated on the kernel ansatz) or 1e3 (strict)
+    const double pf = warp_pfaffian_tiles<MT, SR, false, PHYS>(c, g.m, scratch, sm);
     if (lane == 0) {
       const double v = abs_floor(g.scale * pf, g.floor2);
       g.K[i * g.ldk + j] = v;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(32 * TI * TJ, 1) gram_tiles_flat_kernel(GramTi
       }
     }
     double pf = 1.0;
-    if (!warp_pfaffian_flat_steps<MT, SR>(c, scratch, sm, pf, L)) pf = gram_cell_pivoted<MT, SR>(a, b, g.m, scratch, sm);
+    if (!warp_pfaffian_flat_steps<MT, SR>(c, scratch, sm, pf, L, g.growth)) pf = gram_cell_pivoted<MT, SR>(a, b, g.m, scratch, sm);
     gram_emit(g, i, j, pf);
     __syncwarp();
   }
@@ -288,7 +290,8 @@ static int gram_tiles_launch(const double* cov0, const double* cov1, long long n
   if (int rc = pack(cov0, n0, p0)) return rc;
   if (same) p1 = p0;
   else if (int rc = pack(cov1, n1, p1)) return rc;
-  GramTileArgs g{p0, p1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, g_abs_floor2};
+  GramTileArgs g{p0, p1, n0, n1, d, row_begin, row_end, mode, scale, K, ldk, g_abs_floor2, g_gram_growth};
+  const bool phys = g_gram_growth > kStaticBlockGrowth;  // compile-time bounds of the kernels with a branch per quadruple
   const long long rows = row_end - row_begin;
   auto launch = [&](auto kernel, int ti, int tj, int per_sm, size_t per_warp_doubles) -> int {
     const size_t smem = (size_t)ti * tj * per_warp_doubles * sizeof(double);
@@ -311,8 +314,10 @@ static int gram_tiles_launch(const double* cov0, const double* cov1, long long n
     const char* env = getenv("MCB200_GRAM_FLAT");
     if (d == 8 * MT && (env == nullptr || atoi(env) != 0))
       return launch(gram_tiles_flat_kernel<MT, 0, 2, 4>, 2, 4, 1, GramSmem<MT, 0>::kPerWarp);
+    if (!phys) return launch(gram_tiles_kernel<MT, 1, 3, 4, 1, false>, 3, 4, 1, GramSmem<MT, 1>::kPerWarp);
     return launch(gram_tiles_kernel<MT, 1, 3, 4, 1>, 3, 4, 1, GramSmem<MT, 1>::kPerWarp);
   } else {
+    if (!phys) return launch(gram_tiles_kernel<MT, 0, 2, 8, 1, false>, 2, 8, 2, GramSmem<MT, 0>::kPerWarp);
     return launch(gram_tiles_kernel<MT, 0, 2, 8, 1>, 2, 8, 2, GramSmem<MT, 0>::kPerWarp);
   }
 }

@@ -54,6 +54,9 @@ class NIFKernel(Kernel):
         #: Gram factorises into 2-qubit factors (csrc/gram_blocks.cu); False forces the dense Pfaffian path
         self.use_block_factorisation = True
         self._blocks_train = None
+        #: accuracy / speed of the d <= 64 Gram kernels (ops.gram): "auto" evaluates a sample of the cells with the fast and
+        #: the strict pivot bound and keeps the fast one only if they agree to 1e-11; "fast" / "strict" force one
+        self.gram_pivoting = "auto"
         #: optional list that receives (stage, cuda event) pairs of the multi-GPU Gram build (bench / profiling)
         self.timeline = None
         #: several ranks: every rank evolves only its slice of the samples and the covariances are all-gathered;
@@ -218,11 +221,14 @@ class NIFKernel(Kernel):
         rank, ws = dist_mod.world()
         if ws == 1:
             return _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_REFERENCE,
-                             floor2=self.pfaffian_epsilon)
+                             floor2=self.pfaffian_epsilon, pivoting=self.gram_pivoting)
+
+        # one decision per build (not per row block): every rank and every launch takes the same route
+        growth = _ops._gram_growth_for(cov0, cov1, n0 * n1, self.gram_pivoting)
 
         def rows(s, e, out_rows):
             _ops.gram(cov0, cov1, scale, mode=_ops.GRAM_FULL if full else _ops.GRAM_TRIANGLE, row_range=(s, e),
-                      out=out_rows, rows_only=True, floor2=self.pfaffian_epsilon)
+                      out=out_rows, rows_only=True, floor2=self.pfaffian_epsilon, pivoting=growth)
 
         return self._sharded_gram(rows, n0, n1, full, cov0.device, gather)
 

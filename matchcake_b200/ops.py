@@ -461,13 +461,68 @@ def _gram_buffer(out: Optional[torch.Tensor], n0: int, n1: int, rb: int, re: int
     return torch.zeros((n0, n1), dtype=torch.float64, device=device)
 
 
+GRAM_GROWTH_FAST, GRAM_GROWTH_STRICT = 1e5, 1e3  # include/mcb200.h: mcb200_set_gram_pivot_growth
+_GRAM_AUTO_SAMPLE = 32        # "auto": a sample of 32 x 32 cells is evaluated with both bounds
+_GRAM_AUTO_TOL = 1e-11        # largest relative difference on the sample for which the fast bound is kept
+_GRAM_AUTO_MIN_CELLS = 1 << 16  # below this the strict bound costs nothing worth a decision
+
+
+class gram_pivot_growth:
+    """``with gram_pivot_growth(1e3):`` -- growth bound of the static block pivots of the Gram launches inside the block
+    (per thread; restored on exit)."""
+
+    def __init__(self, growth: float):
+        self.growth = float(growth)
+
+    def __enter__(self):
+        lib = _lib.load()
+        self.prev = float(lib.mcb200_get_gram_pivot_growth())
+        _lib.check(lib.mcb200_set_gram_pivot_growth(self.growth))
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().mcb200_set_gram_pivot_growth(self.prev)
+        return False
+
+
+def _gram_growth_for(cov0: torch.Tensor, cov1: torch.Tensor, cells: int, pivoting) -> float:
+    """``pivoting``: "fast" (bound 1e5: exact to 1e-14 on the covariances of the reference's kernel ansatz, up to 1e-8
+    off in about 1 cell in 1000 for generic Haar-like states), "strict" (1e3: every cell within 1e-11), a number, or
+    "auto": strict for small problems, otherwise a 32 x 32 sample of the cells (evenly spaced rows and columns) is
+    evaluated with both bounds and the fast one is kept only if the two agree to 1e-11 (one small device -> host read)."""
+    if isinstance(pivoting, (int, float)):
+        return float(pivoting)
+    if pivoting == "fast":
+        return GRAM_GROWTH_FAST
+    if pivoting == "strict":
+        return GRAM_GROWTH_STRICT
+    if pivoting != "auto":
+        raise ValueError(f"pivoting must be 'auto', 'fast', 'strict' or a growth bound, got {pivoting!r}")
+    d = cov0.shape[-1]
+    if d > 64 or cells < _GRAM_AUTO_MIN_CELLS:   # d > 64: scalar pivots guarded at 1e-3 of their row, no bound to choose
+        return GRAM_GROWTH_STRICT
+    n0, n1 = cov0.shape[0], cov1.shape[0]
+    i0 = torch.linspace(0, n0 - 1, min(n0, _GRAM_AUTO_SAMPLE), device=cov0.device).round().long()
+    i1 = torch.linspace(0, n1 - 1, min(n1, _GRAM_AUTO_SAMPLE), device=cov0.device).round().long().flip(0)
+    s0, s1 = cov0.index_select(0, i0).contiguous(), cov1.index_select(0, i1).contiguous()
+    both = []
+    for growth in (GRAM_GROWTH_FAST, GRAM_GROWTH_STRICT):
+        k = torch.empty((s0.shape[0], s1.shape[0]), dtype=torch.float64, device=cov0.device)
+        with gram_pivot_growth(growth):
+            _op.gram_out(k, s0, s1, 1.0, GRAM_FULL, 0, s0.shape[0], False, 0.0)
+        both.append(k)
+    fast, strict = both
+    rel = ((fast - strict).abs() / strict.abs().clamp_min(1e-300)).max()
+    return GRAM_GROWTH_FAST if float(rel) <= _GRAM_AUTO_TOL else GRAM_GROWTH_STRICT
+
+
 def gram(cov0: torch.Tensor, cov1: torch.Tensor, scale: float, mode: int = GRAM_REFERENCE,
          row_range: Optional[Tuple[int, int]] = None, out: Optional[torch.Tensor] = None,
-         rows_only: bool = False, floor2: float = 0.0, chunk: int = 8192) -> torch.Tensor:
+         rows_only: bool = False, floor2: float = 0.0, chunk: int = 8192, pivoting="auto") -> torch.Tensor:
     """K[i, j] = scale |Pf(cov0[i] + cov1[j])| with the reference's triangle/mirror/unit-diagonal rules.
     ``floor2`` > 0: evaluated entries are sqrt(K^2 + floor2) (the reference's Gram goes through LookupTableStrategy,
-    i.e. sqrt(|det| + 1e-32), nif_kernel.py:210-221 -> lookup_table_strategy.py:70-71).  Under autograd the cells go
-    through the differentiable Pfaffian op ``chunk`` at a time."""
+    i.e. sqrt(|det| + 1e-32), nif_kernel.py:210-221 -> lookup_table_strategy.py:70-71).  ``pivoting``: see
+    :func:`_gram_growth_for`.  Under autograd the cells go through the differentiable Pfaffian op ``chunk`` at a time."""
     if _ag.needs_grad(cov0, cov1):
         return _gram_differentiable(cov0, cov1, scale, mode, row_range, floor2, chunk)
     cov0, cov1 = _f64(cov0, "cov0"), _f64(cov1, "cov1")
@@ -476,7 +531,11 @@ def gram(cov0: torch.Tensor, cov1: torch.Tensor, scale: float, mode: int = GRAM_
     if rows_only and mode == GRAM_REFERENCE:
         raise ValueError("rows_only needs mode TRIANGLE or FULL (REFERENCE mirrors into rows outside the block)")
     out = _gram_buffer(out, n0, n1, rb, re, rows_only, cov0.device)
-    _op.gram_out(out, cov0, cov1, float(scale), int(mode), int(rb), int(re), bool(rows_only), float(floor2))
+    # the decision looks at the whole problem (n0 x n1), not at this call's rows: every rank of a row-sharded build
+    # takes the same route
+    growth = _gram_growth_for(cov0, cov1, n0 * n1, pivoting) if n0 and n1 else GRAM_GROWTH_STRICT
+    with gram_pivot_growth(growth):
+        _op.gram_out(out, cov0, cov1, float(scale), int(mode), int(rb), int(re), bool(rows_only), float(floor2))
     return out
 
 

@@ -27,6 +27,7 @@ ENTRY_TO_OP = {
     "mcb200_cov_dense_backward": "cov_dense_backward", "mcb200_circuit_columns_backward": "circuit_columns_backward",
 }
 NOT_OPS = {"mcb200_circuit_validate", "mcb200_version", "mcb200_last_error", "mcb200_device_count", "mcb200_set_abs_floor", "mcb200_get_abs_floor",
+           "mcb200_set_gram_pivot_growth", "mcb200_get_gram_pivot_growth",
            "mcb200_set_expval_route", "mcb200_launch_count", "mcb200_reset_launch_count", "mcb200_probe_fp64_tflops"}
 
 
