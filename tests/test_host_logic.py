@@ -266,3 +266,21 @@ def test_strategy_plugin_surface_contract():
     for base in (st.ProbabilityStrategy, st.ExpvalStrategy):
         with pytest.raises(NotImplementedError):
             base()(state_prep_op=None, target_binary_states=None, wires=None) if base is st.ProbabilityStrategy else base()(None, None)
+
+
+def test_gram_pivoting_option_is_parsed_on_the_host():
+    """ops.gram(pivoting=...): the named bounds, an explicit number and the error for anything else are resolved without a
+    launch; "auto" is strict for small problems and for d > 64 (whose kernels use guarded scalar pivots)."""
+    import torch
+
+    from matchcake_b200 import ops as mops
+
+    assert mops._gram_growth_for(None, None, 0, "fast") == mops.GRAM_GROWTH_FAST == 1e5
+    assert mops._gram_growth_for(None, None, 0, "strict") == mops.GRAM_GROWTH_STRICT == 1e3
+    assert mops._gram_growth_for(None, None, 0, 250) == 250.0
+    with pytest.raises(ValueError, match="pivoting must be"):
+        mops._gram_growth_for(None, None, 0, "sometimes")
+    small = torch.zeros((10, 64, 64), dtype=torch.float64)
+    assert mops._gram_growth_for(small, small, 100, "auto") == mops.GRAM_GROWTH_STRICT       # 100 cells: no decision to make
+    wide = torch.zeros((2, 128, 128), dtype=torch.float64)
+    assert mops._gram_growth_for(wide, wide, 1 << 20, "auto") == mops.GRAM_GROWTH_STRICT     # d > 64
