@@ -86,6 +86,31 @@ def test_gram_matrix_rules():
         assert gm.to_tensor().dtype == torch.float32
 
 
+def test_gram_matrix_memmap_store():
+    """gram_matrix.py:25-47 of the reference: float32 entries in a numpy.memmap on a temporary file; same rules, the
+    file holds what the container shows, and it is removed with the container."""
+    import os
+
+    shape = (9, 7)
+    gm = GramMatrix(shape, memmap=True)
+    path = gm._filepath
+    assert os.path.exists(path) and os.path.getsize(path) == 9 * 7 * 4
+    gm.apply_(lambda ids: (ids[:, 0] * 10 + ids[:, 1]).astype(np.float64), batch_size=5)
+    ref = GramMatrix(shape).apply_(lambda ids: (ids[:, 0] * 10 + ids[:, 1]).astype(np.float64), batch_size=5)
+    np.testing.assert_array_equal(gm.to_tensor().numpy(), ref.to_tensor().numpy())
+    on_disk = np.fromfile(path, dtype=np.float32).reshape(shape)
+    np.testing.assert_array_equal(on_disk, ref.to_tensor().numpy())
+    # a finished Gram (here a host tensor standing in for the device one), streamed in row blocks
+    k = torch.arange(63, dtype=torch.float64).reshape(shape) / 7
+    g2 = GramMatrix.from_device(k, memmap=True, rows_per_copy=4)
+    np.testing.assert_array_equal(np.fromfile(g2._filepath, dtype=np.float32).reshape(shape), k.to(torch.float32).numpy())
+    p2 = g2._filepath
+    g2.close()
+    assert not os.path.exists(p2) and g2.to_tensor().shape == shape
+    del gm
+    assert not os.path.exists(path)
+
+
 def test_states_to_binary_msb_first():
     got = NonInteractingFermionicDevice.states_to_binary(np.arange(8), 3)
     np.testing.assert_array_equal(got, oro.states_to_binary(np.arange(8), 3))
