@@ -101,7 +101,7 @@ double mcb200_get_abs_floor(void);
  * `growth`; a cell whose guard fails is computed with partial pivoting instead (slower, accuracy of the reference's LU).
  * The initial value 1e5 is calibrated on the covariances of the reference's kernel ansatz (FermionicPQCKernel,
  * fermionic_pqc_kernel.py:166-199: shallow light cones; worst relative error measured 1e-14).  For covariances of generic
- * (Haar-like) Gaussian states the same bound lets relative errors of up to 1e-8 through in about 1 cell in 1000; 1e3 keeps
+ * (Haar-like) Gaussian states the same bound leaves about 2 % of the cells off by more than 1e-10 (worst 1e-8, profiles/r02/guard_study.txt); 1e3 keeps
  * every cell within 1e-11 of the reference at the price of 10 - 40 % of the cells taking the pivoted route.
  * matchcake_b200.ops.gram(pivoting="auto") decides per call by evaluating a sample of the cells both ways. */
 int mcb200_set_gram_pivot_growth(double growth);

@@ -487,7 +487,7 @@ class gram_pivot_growth:
 
 def _gram_growth_for(cov0: torch.Tensor, cov1: torch.Tensor, cells: int, pivoting) -> float:
     """``pivoting``: "fast" (bound 1e5: exact to 1e-14 on the covariances of the reference's kernel ansatz, up to 1e-8
-    off in about 1 cell in 1000 for generic Haar-like states), "strict" (1e3: every cell within 1e-11), a number, or
+    off in the worst of the ~2 % of cells that miss 1e-10 for generic Haar-like states), "strict" (1e3: every cell within 1e-11), a number, or
     "auto": strict for small problems, otherwise a 32 x 32 sample of the cells (evenly spaced rows and columns) is
     evaluated with both bounds and the fast one is kept only if the two agree to 1e-11 (one small device -> host read)."""
     if isinstance(pivoting, (int, float)):
