@@ -290,3 +290,43 @@ def test_oracle_kernel_equals_dense_statevector_kernel(n, rotations, nf):
     states = [statevector(unbatched(ops, i), n).reshape(-1) for i in range(len(x))]
     ref = np.array([[abs(np.vdot(a, b)) ** 2 for b in states] for a in states])
     np.testing.assert_allclose(got, ref, rtol=0, atol=5e-14)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5])
+def test_oracle_pauli_expvals_equal_dense_statevector(n):
+    """qml.expval(sum of Pauli words) through the extended covariance and the sector Pfaffians
+    (m_pfaffian_expval_strategy.py:270-306, jordan_wigner.py:62-140) against <psi| P |psi> on the dense state vector:
+    every single-qubit letter, odd and even Majorana rank, identity, from random product states whose amplitudes are
+    propagated through a random matchgate circuit (tests/test_devices/test_expval_strategies/test_m_pfaffian/
+    test_m_pfaffian_expval_strategy.py:683-915 does this against default.qubit)."""
+    from tests.helpers import statevector
+
+    paulis = {"I": np.eye(2), "X": np.array([[0, 1], [1, 0]]), "Y": np.array([[0, -1j], [1j, 0]]),
+              "Z": np.array([[1, 0], [0, -1]])}
+    rng = np.random.default_rng(500 + n)
+    for trial in range(3):
+        ops = _random_matchgate_circuit(rng, n, 3 * n)
+        r = gates.chain(ops, n)
+        if trial == 0:
+            amp = cv.amplitudes_from_basis_state(rng.integers(0, 2, n))
+        else:
+            amp = rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))
+            amp /= np.linalg.norm(amp, axis=1, keepdims=True)
+        # product state |phi_0> ... |phi_{n-1}> as the initial dense vector, then the circuit
+        psi0 = np.ones(1, dtype=complex)
+        for q in range(n):
+            psi0 = np.kron(psi0, amp[q])
+        psi = np.zeros(2 ** n, dtype=complex)
+        for b in range(2 ** n):
+            bits = [(b >> (n - 1 - q)) & 1 for q in range(n)]
+            psi += psi0[b] * statevector(ops, n, bits).reshape(-1)
+        words = ["".join(rng.choice(list("IXYZ"), n)) for _ in range(10)] + ["I" * n, "Z" * n, "X" + "I" * (n - 1)]
+        coeffs = rng.standard_normal(len(words))
+        dense = 0.0
+        for w, c in zip(words, coeffs):
+            p = np.ones((1, 1), dtype=complex)
+            for ch in w:
+                p = np.kron(p, paulis[ch])
+            dense += c * np.real(np.vdot(psi, p @ psi))
+        got = readout.expval_pauli_sum(cv.evolved_extended_covariance(amp, r), words, coeffs)
+        np.testing.assert_allclose(float(got), dense, rtol=0, atol=2e-13)
