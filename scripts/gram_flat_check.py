@@ -31,14 +31,14 @@ for key, b in res.items():
     print(key, "vs plain: max rel diff", ((a - b).abs() / (a.abs() + 1e-300)).max().item())
 b = res[list(res)[-1]]
 rel = ((a - b).abs() / (a.abs() + 1e-300)).max().item()
-print("fused vs plain: max rel diff", rel, "max abs diff", (a - b).abs().max().item())
-# against sqrt|det(L_i + L_j)| on a sample of cells (rows 0..63 against everything)
+print("flat vs branchy: max rel diff", rel, "max abs diff", (a - b).abs().max().item())
+# the default (flat) kernel against sqrt|det(L_i + L_j)| on a sample of cells (rows 0..63 against everything)
 m = min(64, n)
 ref = scale * torch.sqrt(torch.abs(torch.linalg.det(cov[:m, None] + cov[None, :])))
 got = b[:m]
 mask = ~torch.eye(n, dtype=torch.bool, device="cuda")[:m]
 err = ((got - ref).abs() / (ref.abs() + 1e-300))[mask]
-print("fused vs det: max rel", err.max().item())
+print("flat vs det: max rel", err.max().item())
 # mirror / diagonal conventions identical
 print("diag equal", torch.equal(a.diagonal(), b.diagonal()), "symmetric", torch.equal(b, b.T))
 assert rel < 1e-11 and err.max().item() < 1e-9
