@@ -237,11 +237,19 @@ def test_gram_identity_covariance_sum():
 
 # ------------------------------------------------------------------ dense state-vector simulation
 def _random_matchgate_circuit(rng, n, n_gates):
+    """Closed-form rotations, fSWAPs and generic matchgates (a product of three rotations, which goes through the trace
+    formula R = 1/4 Tr(U c_mu U^+ c_nu) of utils/__init__.py:561-596 instead of a closed form)."""
     ops = []
     for _ in range(n_gates):
         w = int(rng.integers(0, n - 1))
-        kind = ("CompRxRx", "CompRyRy", "CompRzRz", "fSWAP")[int(rng.integers(0, 4))]
-        ops.append(gates.Op(kind, (w, w + 1), params=None if kind == "fSWAP" else rng.uniform(0, 2 * np.pi, 2)))
+        kind = ("CompRxRx", "CompRyRy", "CompRzRz", "fSWAP", "Matchgate")[int(rng.integers(0, 5))]
+        if kind == "Matchgate":
+            u = gates.matchgate_comp_rotation(rng.uniform(0, 2 * np.pi, 2), "XX") @ \
+                gates.matchgate_comp_rotation(rng.uniform(0, 2 * np.pi, 2), "ZZ") @ \
+                gates.matchgate_comp_rotation(rng.uniform(0, 2 * np.pi, 2), "YY")
+            ops.append(gates.Op(kind, (w, w + 1), matrix=u))
+        else:
+            ops.append(gates.Op(kind, (w, w + 1), params=None if kind == "fSWAP" else rng.uniform(0, 2 * np.pi, 2)))
     return ops
 
 
